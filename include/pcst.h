@@ -1,0 +1,158 @@
+/*
+ * pcst.h -- C ABI of libpcst.so: B200 (sm_100a) kernels for the point-set hot path of
+ * wangxy0820/PointCloud_style_transfer.
+ *
+ * The reference has no FFI layer: its boundary is the Python symbol surface of
+ *   models/pointnet2_encoder.py, models/losses.py, evaluation/metrics.py and
+ *   models/diffusion_model.py::HierarchicalProcessor.upsample_knn      (SURVEY.md §8(b)).
+ * Each entry point below names the reference function (file:line, relative to the reference
+ * root) whose arithmetic it replaces.  The Python package pointcloud_style_transfer_b200 binds
+ * these symbols with ctypes and re-exposes them as torch custom ops (pcst::*) behind the
+ * reference's own function / class names; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - Every function returns an int status: 0 = PCST_OK, negative = error.  Nothing throws across
+ *    the ABI.  pcst_last_error() returns a thread-local, human-readable message for the last
+ *    non-zero status on the calling thread.
+ *  - All data pointers are DEVICE pointers on the current CUDA device, contiguous in the stated
+ *    row-major layout.  Floating data are fp32 unless stated, indices are int64 (the reference's
+ *    dtypes).  The caller owns every buffer: the library never allocates, frees or retains
+ *    device memory.  Scratch space is passed in as (ws, ws_bytes); query the size with the
+ *    matching *_workspace_bytes() function.  ws must be 256-byte aligned.
+ *  - Kernels are launched on the cudaStream_t passed as `stream` (a void* here so that the header
+ *    needs no CUDA include); calls are stream-ordered, asynchronous and re-entrant.  There are no
+ *    implicit device synchronisations and no host<->device copies.
+ *  - There is no CPU fallback.  On a device that is not compute capability 10.x every compute
+ *    entry point returns PCST_ERR_UNSUPPORTED.
+ */
+#ifndef PCST_H_
+#define PCST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCST_OK 0
+#define PCST_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, k out of range ...) */
+#define PCST_ERR_UNSUPPORTED (-2) /* shape / device outside what the kernels support */
+#define PCST_ERR_CUDA (-3)        /* a CUDA runtime call or launch failed; see pcst_last_error() */
+#define PCST_ERR_WORKSPACE (-4)   /* ws_bytes smaller than *_workspace_bytes() or ws misaligned */
+
+typedef void* pcst_stream_t; /* cudaStream_t */
+
+const char* pcst_version(void);
+const char* pcst_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), else PCST_ERR_UNSUPPORTED. */
+int pcst_device_check(void);
+/* Internal tuning knobs (kernel variant selection for benchmarking sweeps); unknown keys -> PCST_ERR_INVALID. */
+int pcst_set_tuning(const char* key, int value);
+int pcst_get_tuning(const char* key, int* value);
+
+/* ---- farthest_point_sample: models/pointnet2_encoder.py:30-45 --------------------------------
+ * xyz [B,N,3]; start [B] = the start index per cloud (the reference draws it with torch.randint
+ * on the CPU generator, :36 -- that draw stays in the caller); out [B,npoint] int64.
+ * new_xyz (optional, may be NULL) [B,npoint,3] receives xyz[b, out[b,i], :], i.e. the
+ * index_points(xyz, fps_idx) of SetAbstraction.forward (:92), at no extra cost.
+ * One persistent thread-block cluster per cloud; points and running distances stay on chip. */
+size_t pcst_fps_workspace_bytes(int B, int N, int npoint);
+int pcst_fps_f32(const float* xyz, int B, int N, int npoint, const int64_t* start, int64_t* out,
+                 float* new_xyz, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
+/* ---- query_ball_point: models/pointnet2_encoder.py:47-59 --------------------------------------
+ * xyz [B,N,3], new_xyz [B,S,3] -> out [B,S,nsample] int64: the first nsample indices j (ascending)
+ * with NOT(sqrdist(new_xyz_s, xyz_j) > radius_sq), sqrdist in the reference's expanded fp32 form;
+ * short rows padded with the row's first index, empty rows filled with N.
+ * radius_sq must be fp32(radius ** 2) exactly as torch's type promotion produces it (:54).
+ * Requires 1 <= nsample <= N (the reference raises IndexError for nsample > N, :58). */
+size_t pcst_ball_query_workspace_bytes(int B, int N, int S);
+int pcst_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int S, float radius_sq,
+                        int nsample, int64_t* out, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
+/* ---- square_distance: models/pointnet2_encoder.py:8-15 ----------------------------------------
+ * src [B,N,3], dst [B,M,3] -> out [B,N,M] = ((-2 * dot) + |src|^2) + |dst|^2, bit-exact with the
+ * reference's fp32 CPU result.  (The fused kernels never materialise this matrix; the entry point
+ * exists because the function is part of the reference's public surface.) */
+int pcst_square_distance_f32(const float* src, const float* dst, int B, int N, int M, float* out,
+                             pcst_stream_t stream);
+
+/* ---- index_points: models/pointnet2_encoder.py:17-28 -------------------------------------------
+ * points [B,N,C], idx [B,S] (any trailing index shape flattened to S) -> out [B,S,C];
+ * indices are clamped to [0, N-1] (:26).  _bwd accumulates grad_out [B,S,C] into grad_points
+ * [B,N,C], which the caller has zero-initialised (autograd of the advanced indexing at :27). */
+int pcst_index_points_f32(const float* points, const int64_t* idx, int B, int N, int C, int S,
+                          float* out, pcst_stream_t stream);
+int pcst_index_points_bwd_f32(const float* grad_out, const int64_t* idx, int B, int N, int C, int S,
+                              float* grad_points, pcst_stream_t stream);
+
+/* ---- grouping of SetAbstraction.forward: models/pointnet2_encoder.py:94-101 --------------------
+ * out [B,S,K,3+D] = cat([xyz[idx] - new_xyz[:, :, None, :], feats[idx]], -1); feats may be NULL (D=0).
+ * xyz [B,N,3], feats [B,N,D], new_xyz [B,S,3], idx [B,S,K] (clamped like index_points). */
+int pcst_group_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
+                   int B, int N, int S, int K, int D, float* out, pcst_stream_t stream);
+
+/* ---- SetAbstraction.apply_mlp: models/pointnet2_encoder.py:106-112 (eval-mode BatchNorm) --------
+ * Fused grouping gather + 3 x relu(bn(conv1x1(.))) + max over the K samples of each group.
+ *   xyz [B,N,3], feats [B,N,D] or NULL, new_xyz [B,S,3] or NULL, idx [B,S,K] int64 or NULL.
+ *   idx == NULL means group_all (:81-89): S = 1, K = N, the "group" is the whole cloud in order and
+ *   no centroid is subtracted.
+ * Layer l (l = 0..2): weight w[l] [Cout_l, Cin_l] fp32 row-major (the Conv2d weight [Cout,Cin,1,1]),
+ *   scale[l], shift[l] [Cout_l]: y = relu(scale * (w . x) + shift), i.e. conv bias and eval-mode BN
+ *   folded by the caller: scale = gamma / sqrt(var + eps), shift = (bias - mean) * scale + beta.
+ *   Cin_0 = 3 + D, Cin_l = Cout_{l-1}.  Supported: Cout_l multiple of 32, Cout_l <= 1024.
+ * out [B, Cout_2, S] (channel-first, the reference's layout).
+ * precision: 0 = fp32 CUDA-core path; 1 = bf16 tcgen05/TMEM tensor-core path (fp32 accumulate). */
+typedef struct {
+    const float* w[3];
+    const float* scale[3];
+    const float* shift[3];
+    int cout[3];
+} pcst_mlp3_t;
+size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp, int precision);
+int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
+                        int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp, int precision,
+                        float* out, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
+/* ---- nearest-neighbour minimum reduction ------------------------------------------------------
+ * a [B,N,3], b [B,M,3] -> rowmin [B,N] = min_j D(a_i, b_j), rowarg [B,N] (optional, may be NULL) =
+ * the lowest j attaining it.
+ *  form 0: models/losses.py:36-41,53-58 -- D = clamp((|a|^2 + |b|^2) + (-2 * dot), min=0), squared
+ *          distances; bit-exact with the reference's fp32 CPU per-point minima.  The second
+ *          direction of the Chamfer loss is the same call with a and b swapped.
+ *  form 1: evaluation/metrics.py:32 -- torch.cdist(a, b, p=2) row minima (Euclidean; ATen's
+ *          mm path [-2a,|a|^2,1].[b,1,|b|^2], clamp_min(0), sqrt), a = cdist's x1.
+ *  form 2: column minima of the same cdist matrix (evaluation/metrics.py:40): a = cdist's x2,
+ *          b = cdist's x1. */
+size_t pcst_nn_min_workspace_bytes(int B, int N, int M);
+int pcst_nn_min_f32(const float* a, const float* b, int B, int N, int M, int form, float* rowmin,
+                    int64_t* rowarg, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
+/* Backward of chamfer_distance_chunked_optimized (autograd of models/losses.py:24-61).
+ * pred [B,N,3], target [B,M,3]; arg_pt [B,N] / arg_tp [B,M] = the argmins returned by pcst_nn_min_f32
+ * (form 0) for pred->target / target->pred; grad_out [B] = dL/d(chamfer[b]).
+ * grad_pred [B,N,3], grad_target [B,M,3] are OVERWRITTEN (zeroed inside, then accumulated). */
+int pcst_chamfer_bwd_f32(const float* pred, const float* target, const int64_t* arg_pt,
+                         const int64_t* arg_tp, const float* grad_out, int B, int N, int M,
+                         float* grad_pred, float* grad_target, pcst_stream_t stream);
+
+/* ---- k nearest neighbours: sklearn NearestNeighbors(n_neighbors=k).kneighbors ------------------
+ * call sites models/diffusion_model.py:146-147, evaluation/metrics.py:126-127,152-153.
+ * query [B,Q,3], ref [B,R,3] fp32 -> idx [B,Q,k] int64, dist [B,Q,k] fp64 ascending (Euclidean);
+ * distances are evaluated in fp64 as sqrt(((dx*dx)+(dy*dy))+(dz*dz)), ties to the lower index.
+ * 1 <= k <= 16, k <= R. */
+size_t pcst_knn_workspace_bytes(int B, int Q, int R, int k);
+int pcst_knn_f32(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx,
+                 double* dist, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
+/* ---- inverse-distance interpolation of HierarchicalProcessor.upsample_knn ----------------------
+ * models/diffusion_model.py:148-150: w = 1/(dist + 1e-8), w /= sum_k w, out = sum_k w_k * feat[idx_k],
+ * evaluated in fp64 and rounded to fp32 once.  feat [B,R,C], idx/dist [B,Q,k] -> out [B,Q,C]. */
+int pcst_knn_interpolate_f32(const float* feat, const int64_t* idx, const double* dist, int B, int R,
+                             int Q, int k, int C, float* out, pcst_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCST_H_ */

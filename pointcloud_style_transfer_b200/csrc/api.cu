@@ -1,0 +1,121 @@
+// api.cu -- error plumbing, device check, tuning knobs and the point-packing pre-pass.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace pcst {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return PCST_OK;
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return PCST_ERR_CUDA;
+}
+
+static std::mutex g_tune_mu;
+static std::map<std::string, int>& tune_map() {
+    static std::map<std::string, int> m = {
+        {"nn_min.variant", 0},        // 0 = auto
+        {"nn_min.splits", 0},         // 0 = auto (candidate-range splits per row tile)
+        {"fps.cluster", 0},           // 0 = auto (CTAs per cloud)
+        {"ball_query.warps", 0},      // 0 = auto (queries per CTA)
+        {"sa_mlp.variant", 0},
+    };
+    return m;
+}
+
+int tuning(const char* key, int dflt) {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    auto it = tune_map().find(key);
+    if (it == tune_map().end() || it->second == 0) return dflt;
+    return it->second;
+}
+
+// ---- pack: [B,N,3] fp32 -> [B,Npad] float4 (x, y, z, |p|^2), sentinel-padded -----------------
+// HBM-bound, 12 B read + 16 B written per point; ~2 MB per 120k-point scan.
+__global__ void pack_points_kernel(const float* __restrict__ xyz, int N, int Npad, float4* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float* src = xyz + (size_t)b * N * 3;
+    float4* dst = out + (size_t)b * Npad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += gridDim.x * blockDim.x) {
+        float4 v;
+        if (i < N) {
+            v.x = src[3 * i];
+            v.y = src[3 * i + 1];
+            v.z = src[3 * i + 2];
+            v.w = norm3_sq(v.x, v.y, v.z);
+        } else {
+            v = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+        }
+        dst[i] = v;
+    }
+}
+
+int launch_pack(const float* xyz, int B, int N, int Npad, float4* out, cudaStream_t stream) {
+    int blocks = (Npad + 255) / 256;
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    pack_points_kernel<<<dim3(blocks, B), 256, 0, stream>>>(xyz, N, Npad, out);
+    return check_cuda(cudaGetLastError(), "pack_points_kernel");
+}
+
+}  // namespace pcst
+
+extern "C" {
+
+const char* pcst_version(void) { return "pcst 0.1.0 (sm_100a)"; }
+
+const char* pcst_last_error(void) { return pcst::g_err; }
+
+int pcst_device_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        pcst::set_error("pcst_device_check: no CUDA device");
+        return PCST_ERR_UNSUPPORTED;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+        pcst::set_error("pcst_device_check: compute capability %d.x, libpcst needs 10.x (sm_100a)", major);
+        return PCST_ERR_UNSUPPORTED;
+    }
+    return PCST_OK;
+}
+
+int pcst_set_tuning(const char* key, int value) {
+    if (!key) return PCST_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(pcst::g_tune_mu);
+    auto it = pcst::tune_map().find(key);
+    if (it == pcst::tune_map().end()) {
+        pcst::set_error("pcst_set_tuning: unknown key '%s'", key);
+        return PCST_ERR_INVALID;
+    }
+    it->second = value;
+    return PCST_OK;
+}
+
+int pcst_get_tuning(const char* key, int* value) {
+    if (!key || !value) return PCST_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(pcst::g_tune_mu);
+    auto it = pcst::tune_map().find(key);
+    if (it == pcst::tune_map().end()) {
+        pcst::set_error("pcst_get_tuning: unknown key '%s'", key);
+        return PCST_ERR_INVALID;
+    }
+    *value = it->second;
+    return PCST_OK;
+}
+
+}  // extern "C"

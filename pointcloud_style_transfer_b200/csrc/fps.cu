@@ -1,0 +1,274 @@
+// fps.cu -- farthest point sampling, one persistent thread-block cluster per cloud (sm_100a).
+//
+// Replaces the npoint x (gather, sub/pow/sum, <, masked index_put, max) launch train of
+// models/pointnet2_encoder.py:38-44 (about 7 launches and one host sync per iteration) with a
+// single launch per batch.  The cloud is split over the CTAs of a cluster (up to 16, the
+// non-portable maximum); every thread keeps P points (x, y, z) and their running minimum
+// distance in registers for the whole kernel, so HBM is touched once (N*12 B in, npoint*8 B out).
+// Per iteration: packed fp32x2 distance update -> per-thread argmax -> REDUX warp argmax ->
+// shared-memory block argmax -> DSMEM all-to-all of (value, index, xyz) by st.async, completion
+// counted on a per-CTA mbarrier (no barrier.cluster / MEMBAR.GPU in the loop).
+//
+// Arithmetic (bit-exact with the reference's fp32 CPU path):
+//   d = ((dx*dx) + (dy*dy)) + (dz*dz), no FMA;  dist = min(dist, d), dist0 = 1e10;
+//   next = argmax(dist), lowest index among equal maxima.
+// Running distances are >= +0, so their IEEE bit patterns order like signed integers; padding
+// slots hold -1.0f and never win.  NaN / Inf coordinates are outside the contract.
+#include "common.cuh"
+
+namespace pcst {
+
+constexpr int kFpsThreads = 512;
+constexpr int kFpsWarps = kFpsThreads / 32;
+constexpr int kFpsMaxCluster = 16;
+constexpr unsigned kNoIdx = 0xffffffffu;
+
+struct FpsShared {
+    int2 wslot[2][kFpsWarps];          // per-warp (value bits, index), double-buffered by iteration parity
+    float4 cslot[2][kFpsMaxCluster];   // per-CTA (x, y, z, value) of the CTA's best point
+    unsigned cidx[2][kFpsMaxCluster];  // per-CTA index of the CTA's best point
+    uint64_t cbar[2];                  // transaction barriers: C x 20 bytes land per use
+};
+
+// P > 0: register-resident, P points per thread (P even).  P == 0: streaming fallback for clouds
+// that do not fit the register file of one cluster: distances live in a global workspace and the
+// points are re-read (from L2) every iteration.
+template <int P>
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __restrict__ start,
+           int64_t* __restrict__ out, float* __restrict__ new_xyz, int pts_per_cta, float* __restrict__ dist_ws) {
+    extern __shared__ __align__(16) float smem_pts[];  // P > 0: SoA copy of this CTA's points
+    __shared__ FpsShared sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned C = cluster_nctarank();
+    const unsigned rank = cluster_ctarank();
+    const int b = blockIdx.x / C;
+    const float* pts = xyz + (size_t)b * N * 3;
+    const int base = rank * pts_per_cta;
+    int count = N - base;
+    if (count > pts_per_cta) count = pts_per_cta;
+    if (count < 0) count = 0;
+    float* sx = smem_pts;
+    float* sy = smem_pts + pts_per_cta;
+    float* sz = smem_pts + 2 * pts_per_cta;
+    float* gdist = (P == 0) ? dist_ws + (size_t)b * N + base : nullptr;
+
+    constexpr int PP = P > 0 ? P / 2 : 1;
+    float2 px[PP], py[PP], pz[PP], pd[PP];
+    if (P > 0) {
+#pragma unroll
+        for (int k = 0; k < PP; ++k) {
+            float v[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int l = (2 * k + h) * kFpsThreads + tid;
+                if (l < count) {
+                    const float* q = pts + (size_t)(base + l) * 3;
+                    v[h][0] = q[0]; v[h][1] = q[1]; v[h][2] = q[2]; v[h][3] = 1e10f;
+                    sx[l] = v[h][0]; sy[l] = v[h][1]; sz[l] = v[h][2];
+                } else {
+                    v[h][0] = v[h][1] = v[h][2] = 0.f; v[h][3] = -1.0f;
+                }
+            }
+            px[k] = make_float2(v[0][0], v[1][0]);
+            py[k] = make_float2(v[0][1], v[1][1]);
+            pz[k] = make_float2(v[0][2], v[1][2]);
+            pd[k] = make_float2(v[0][3], v[1][3]);
+        }
+    } else {
+        for (int l = tid; l < count; l += kFpsThreads) gdist[l] = 1e10f;
+    }
+
+    long long far = start[b];
+    if (far < 0) far = 0;
+    if (far >= N) far = N - 1;
+    float cx = pts[3 * far], cy = pts[3 * far + 1], cz = pts[3 * far + 2];
+    if (tid == 0) {
+        mbar_init(&sh.cbar[0], 1);
+        mbar_init(&sh.cbar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (C > 1) cluster_sync_all();  // every CTA is resident and its barriers are initialised before DSMEM traffic
+
+    for (int it = 0; it < npoint; ++it) {
+        if (rank == 0 && tid == 0) {
+            out[(size_t)b * npoint + it] = far;
+            if (new_xyz) {
+                float* o = new_xyz + ((size_t)b * npoint + it) * 3;
+                o[0] = cx; o[1] = cy; o[2] = cz;
+            }
+        }
+        if (it == npoint - 1) break;
+        const int par = it & 1;
+
+        // ---- distance update + per-thread argmax (ascending index, strict > keeps the lowest) ----
+        float best = -1.0f;
+        unsigned bi = kNoIdx;
+        if (P > 0) {
+            const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+#pragma unroll
+            for (int k = 0; k < PP; ++k) {
+                const float2 dx = __fadd2_rn(px[k], ncx), dy = __fadd2_rn(py[k], ncy), dz = __fadd2_rn(pz[k], ncz);
+                const float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+                pd[k].x = fminf(pd[k].x, d.x);
+                pd[k].y = fminf(pd[k].y, d.y);
+                if (pd[k].x > best) { best = pd[k].x; bi = base + (2 * k) * kFpsThreads + tid; }
+                if (pd[k].y > best) { best = pd[k].y; bi = base + (2 * k + 1) * kFpsThreads + tid; }
+            }
+        } else {
+            for (int l = tid; l < count; l += kFpsThreads) {
+                const float* q = pts + (size_t)(base + l) * 3;
+                const float dx = __fsub_rn(q[0], cx), dy = __fsub_rn(q[1], cy), dz = __fsub_rn(q[2], cz);
+                const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                const float cur = fminf(gdist[l], d);
+                gdist[l] = cur;
+                if (cur > best) { best = cur; bi = base + l; }
+            }
+        }
+
+        // ---- warp argmax: two REDUX instead of a 5-step shuffle tree ----
+        const int vb = __float_as_int(best);
+        const int wmax = __reduce_max_sync(0xffffffffu, vb);
+        const unsigned widx = __reduce_min_sync(0xffffffffu, vb == wmax ? bi : kNoIdx);
+        if (lane == 0) sh.wslot[par][warp] = make_int2(wmax, (int)widx);
+        __syncthreads();
+
+        // ---- block argmax, computed redundantly by every warp ----
+        int2 e = lane < kFpsWarps ? sh.wslot[par][lane] : make_int2((int)0x80000000, (int)kNoIdx);
+        const int bmax = __reduce_max_sync(0xffffffffu, e.x);
+        const unsigned bidx = __reduce_min_sync(0xffffffffu, e.x == bmax ? (unsigned)e.y : kNoIdx);
+
+        if (C == 1) {
+            far = bidx;
+            if (P > 0) {
+                const int l = (int)bidx - base;
+                cx = sx[l]; cy = sy[l]; cz = sz[l];
+            } else {
+                const float* q = pts + (size_t)bidx * 3;
+                cx = q[0]; cy = q[1]; cz = q[2];
+            }
+        } else {
+            // ---- cluster argmax: each CTA pushes its best (xyz, value, index) into every CTA's slot with
+            // st.async; the 20 bytes per sender complete a transaction count on the receiver's mbarrier.
+            // Buffer `par` is reused every second iteration; its k-th use is phase k of cbar[par].
+            if (tid == 0) mbar_arrive_expect_tx(&sh.cbar[par], 20u * C);
+            if (warp == 0 && lane < (int)C) {
+                float x = 0.f, y = 0.f, z = 0.f;
+                if (bidx != kNoIdx) {
+                    if (P > 0) {
+                        const int l = (int)bidx - base;
+                        x = sx[l]; y = sy[l]; z = sz[l];
+                    } else {
+                        const float* q = pts + (size_t)bidx * 3;
+                        x = q[0]; y = q[1]; z = q[2];
+                    }
+                }
+                const uint32_t rbar = mapa_shared(smem_u32(&sh.cbar[par]), lane);
+                asm volatile(
+                    "st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                        mapa_shared(smem_u32(&sh.cslot[par][rank]), lane)),
+                    "f"(x), "f"(y), "f"(z), "f"(__int_as_float(bmax)), "r"(rbar)
+                    : "memory");
+                asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(
+                                 mapa_shared(smem_u32(&sh.cidx[par][rank]), lane)),
+                             "r"(bidx), "r"(rbar)
+                             : "memory");
+            }
+            mbar_wait(&sh.cbar[par], (uint32_t)((it >> 1) & 1));
+            float4 a = make_float4(0.f, 0.f, 0.f, -1.0f);
+            unsigned ii = kNoIdx;
+            if (lane < (int)C) {
+                a = sh.cslot[par][lane];
+                ii = sh.cidx[par][lane];
+            }
+            const int gb = __float_as_int(a.w);
+            const int gmax = __reduce_max_sync(0xffffffffu, gb);
+            const unsigned gidx = __reduce_min_sync(0xffffffffu, gb == gmax ? ii : kNoIdx);
+            const unsigned hit = __ballot_sync(0xffffffffu, ii == gidx);
+            const int wl = __ffs(hit) - 1;
+            cx = __shfl_sync(0xffffffffu, a.x, wl);
+            cy = __shfl_sync(0xffffffffu, a.y, wl);
+            cz = __shfl_sync(0xffffffffu, a.z, wl);
+            far = gidx;
+        }
+    }
+    // Every CTA has received all C messages of the last exchange before it gets here, so no peer
+    // writes into an exited CTA's shared memory.
+}
+
+struct FpsPlan {
+    int C, P, pts_per_cta;
+    size_t smem, ws;
+};
+
+static FpsPlan fps_plan(int B, int N) {
+    FpsPlan p;
+    int C = tuning("fps.cluster", 0);
+    if (C == 0) C = N <= 4096 ? 1 : (N <= 16384 ? 4 : (N <= 65536 ? 8 : 16));
+    if (C > kFpsMaxCluster) C = kFpsMaxCluster;
+    p.C = C;
+    int per = (N + C - 1) / C;
+    per = (int)align_up((size_t)per, 32);
+    p.pts_per_cta = per;
+    p.P = per <= 2 * kFpsThreads ? 2 : per <= 4 * kFpsThreads ? 4 : per <= 8 * kFpsThreads ? 8
+          : per <= 16 * kFpsThreads ? 16 : 0;
+    p.smem = p.P > 0 ? (size_t)3 * per * sizeof(float) : 0;
+    p.ws = p.P > 0 ? 0 : align_up((size_t)B * N * sizeof(float), 256);
+    return p;
+}
+
+template <int P>
+static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoint, const int64_t* start,
+                      int64_t* out, float* new_xyz, float* dist_ws, cudaStream_t stream) {
+    auto kern = fps_kernel<P>;
+    if (p.smem > 48 * 1024)
+        PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    if (p.C > 8) PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * p.C);
+    cfg.blockDim = dim3(kFpsThreads);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int pts_per_cta = p.pts_per_cta;
+    PCST_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, out, new_xyz, pts_per_cta, dist_ws));
+    return PCST_OK;
+}
+
+}  // namespace pcst
+
+using namespace pcst;
+
+extern "C" size_t pcst_fps_workspace_bytes(int B, int N, int npoint) {
+    (void)npoint;
+    if (B <= 0 || N <= 0) return 0;
+    return fps_plan(B, N).ws;
+}
+
+extern "C" int pcst_fps_f32(const float* xyz, int B, int N, int npoint, const int64_t* start, int64_t* out,
+                            float* new_xyz, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCST_CHECK_ARG(xyz && start && out, "null pointer");
+    PCST_CHECK_ARG(B > 0 && N > 0 && npoint > 0, "B, N, npoint must be positive");
+    const FpsPlan p = fps_plan(B, N);
+    if (p.ws > 0 && (!ws || ws_bytes < p.ws || ((uintptr_t)ws & 255))) {
+        set_error("pcst_fps_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, p.ws);
+        return PCST_ERR_WORKSPACE;
+    }
+    float* dist_ws = (float*)ws;
+    switch (p.P) {
+        case 2: return fps_launch<2>(p, xyz, B, N, npoint, start, out, new_xyz, dist_ws, stream);
+        case 4: return fps_launch<4>(p, xyz, B, N, npoint, start, out, new_xyz, dist_ws, stream);
+        case 8: return fps_launch<8>(p, xyz, B, N, npoint, start, out, new_xyz, dist_ws, stream);
+        case 16: return fps_launch<16>(p, xyz, B, N, npoint, start, out, new_xyz, dist_ws, stream);
+        default: return fps_launch<0>(p, xyz, B, N, npoint, start, out, new_xyz, dist_ws, stream);
+    }
+}

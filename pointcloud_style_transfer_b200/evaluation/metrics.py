@@ -1,0 +1,66 @@
+"""Drop-in for the nearest-neighbour metrics of the reference's ``evaluation/metrics.py`` on B200."""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+class PointCloudMetrics:
+    """evaluation/metrics.py:14-203.  chamfer / hausdorff / coverage / uniformity run on the NN-min
+    and kNN kernels (no [B,N,M] matrix, no sklearn, no host round trip); ``fidelity_score`` is the
+    reference's few lines of torch; ``earth_mover_distance`` (a greedy O(N^2) Python loop, not an NN
+    reduction) is out of scope."""
+
+    def __init__(self, device: str = 'cuda'):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PointCloudMetrics: a CUDA device (B200) is required; there is no CPU fallback")
+        self.device = torch.device(device)
+
+    def chamfer_distance(self, pred: torch.Tensor, target: torch.Tensor, bidirectional: bool = True) -> torch.Tensor:
+        """evaluation/metrics.py:20-44: Euclidean (un-squared) NN distances of torch.cdist, (mean+mean)/2."""
+        d1, _ = ops.nn_min(pred, target, 1, False)
+        c1 = torch.mean(d1, dim=1)
+        if bidirectional:
+            d2, _ = ops.nn_min(target, pred, 2, False)
+            return (c1 + torch.mean(d2, dim=1)) / 2
+        return c1
+
+    def hausdorff_distance(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """evaluation/metrics.py:90-105."""
+        d1, _ = ops.nn_min(pred, target, 1, False)
+        d2, _ = ops.nn_min(target, pred, 2, False)
+        return torch.max(torch.max(d1, dim=1)[0], torch.max(d2, dim=1)[0])
+
+    def coverage_score(self, pred: torch.Tensor, target: torch.Tensor, threshold: float = 0.01) -> float:
+        """evaluation/metrics.py:107-134: share of target points whose nearest pred point (fp64, as
+        sklearn) is closer than ``threshold``, averaged over the batch."""
+        dist, _ = ops.knn(target, pred, 1)
+        covered = (dist[..., 0] < threshold).sum(dim=1).double() / target.shape[1]
+        return float(covered.mean().item())
+
+    def uniformity_score(self, points: torch.Tensor, k: int = 8) -> float:
+        """evaluation/metrics.py:136-170: 1 / (1 + cv) of the mean distance to the k nearest other points."""
+        dist, _ = ops.knn(points, points, k + 1)
+        mean_d = dist[..., 1:].mean(dim=2)                      # [B,N], self (column 0) dropped
+        std, mean = mean_d.std(dim=1, unbiased=False), mean_d.mean(dim=1)
+        score = torch.where(mean > 0, 1.0 / (1.0 + std / mean), torch.zeros_like(mean))
+        return float(score.mean().item())
+
+    def earth_mover_distance(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("earth_mover_distance (evaluation/metrics.py:46-88) is a greedy O(N^2) host loop, "
+                                  "not an NN reduction; out of scope of this path (SURVEY.md §2 row 3)")
+
+    def fidelity_score(self, pred: torch.Tensor, target: torch.Tensor,
+                       feature_extractor: Optional[nn.Module] = None) -> float:
+        """evaluation/metrics.py:172-203 (plain torch statistics / the caller's feature extractor)."""
+        if feature_extractor is None:
+            pred_feat = torch.cat([pred.mean(dim=1), pred.std(dim=1)], dim=1)
+            target_feat = torch.cat([target.mean(dim=1), target.std(dim=1)], dim=1)
+        else:
+            with torch.no_grad():
+                pred_feat = feature_extractor(pred)
+                target_feat = feature_extractor(target)
+        return F.cosine_similarity(pred_feat, target_feat, dim=1).mean().item()

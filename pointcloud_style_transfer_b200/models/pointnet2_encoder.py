@@ -1,0 +1,204 @@
+"""Drop-in for the reference's ``models/pointnet2_encoder.py`` on B200.
+
+Same names, signatures, tensor layouts, index dtypes and ``state_dict`` keys as the reference
+(file:line citations are relative to the reference root); the arithmetic runs in the sm_100a
+kernels of libpcst.so through the ``pcst::*`` custom ops.  CUDA tensors only -- no CPU fallback.
+"""
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+def _cuda_only(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor; pointcloud_style_transfer_b200 has no CPU fallback")
+
+
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """models/pointnet2_encoder.py:8-15.  [B,N,3], [B,M,3] -> [B,N,M] fp32, bit-exact with the
+    reference's fp32 CPU result (always fp32: the op opts out of autocast)."""
+    _cuda_only(src, "square_distance")
+    return ops.square_distance(src, dst)
+
+
+def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """models/pointnet2_encoder.py:17-28.  points [B,N,C], idx [B,S] or [B,S,K] (clamped to
+    [0, N-1]) -> [B,S,C] / [B,S,K,C]; differentiable w.r.t. ``points``."""
+    _cuda_only(points, "index_points")
+    return ops.index_points(points, idx)
+
+
+def farthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    """models/pointnet2_encoder.py:30-45.  xyz [B,N,3] -> [B,npoint] int64.
+
+    The start index is drawn exactly like the reference does (:36): ``torch.randint`` on the CPU
+    default generator, then moved to the device, so a seeded run consumes the same RNG stream."""
+    _cuda_only(xyz, "farthest_point_sample")
+    B, N, _ = xyz.shape
+    farthest = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
+    idx, _ = ops.fps(xyz, int(npoint), farthest)
+    return idx
+
+
+def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """models/pointnet2_encoder.py:47-59.  -> [B,S,nsample] int64.  ``radius ** 2`` is rounded to
+    fp32 as torch's type promotion does at :54.  Like the reference, nsample > N raises IndexError."""
+    _cuda_only(xyz, "query_ball_point")
+    if nsample > xyz.shape[1]:
+        raise IndexError(f"query_ball_point: nsample={nsample} exceeds the number of points N={xyz.shape[1]} "
+                         "(the reference raises IndexError at models/pointnet2_encoder.py:58)")
+    return ops.ball_query(xyz, new_xyz, float(np.float32(float(radius) ** 2)), int(nsample))
+
+
+class SetAbstraction(nn.Module):
+    """models/pointnet2_encoder.py:61-112.  Parameters live in the same ``mlp_convs`` / ``mlp_bns``
+    ModuleLists (Conv2d 1x1 + BatchNorm2d) so reference checkpoints load unchanged.
+
+    Inference (``eval()`` and no gradient required) takes the fused path: FPS (+ centroid gather) ->
+    ball query -> one fused gather + MLP + max-pool op with conv bias and BatchNorm folded.
+    Training / gradient mode composes the differentiable ``pcst`` gather ops with torch's own
+    Conv2d / BatchNorm2d (batch statistics, running-stat updates and autograd exactly as the
+    reference; those dense layers run on cuBLAS/cuDNN -- library code)."""
+
+    #: 0 = fp32 CUDA-core MLP (exact-parity path), 1 = bf16 tcgen05 tensor-core MLP
+    mlp_precision: int = 0
+
+    def __init__(self, npoint: int, radius: float, nsample: int,
+                 in_channel: int, mlp: List[int], group_all: bool = False):
+        super().__init__()
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last_channel = in_channel + 3
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last_channel, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last_channel = out_channel
+        self.group_all = group_all
+        self._fold_key = None
+        self._fold = None
+
+    # -- eval-mode folding of conv bias + BatchNorm into per-channel (scale, shift) ------------------
+    def _folded(self):
+        tensors = []
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        if key != self._fold_key:
+            ws, scs, shs = [], [], []
+            cin_pad = 0
+            with torch.no_grad():
+                for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+                    w = conv.weight.detach().reshape(conv.out_channels, -1).float()
+                    scale = (bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps))
+                    shift = (conv.bias.double() - bn.running_mean.double()) * scale + bn.bias.double()
+                    if cin_pad:  # previous layer was padded: its extra channels are identically 0
+                        w = F.pad(w, (0, cin_pad))
+                    cout_pad = (-conv.out_channels) % 32  # kernels need Cout % 32 == 0
+                    if cout_pad:
+                        w = F.pad(w, (0, 0, 0, cout_pad))
+                        scale = F.pad(scale, (0, cout_pad))
+                        shift = F.pad(shift, (0, cout_pad))
+                    ws.append(w.contiguous())
+                    scs.append(scale.float().contiguous())
+                    shs.append(shift.float().contiguous())
+                    cin_pad = cout_pad
+            self._fold, self._fold_key = (ws, scs, shs), key
+        return self._fold
+
+    def _fused_ok(self, *tensors) -> bool:
+        if self.training or len(self.mlp_convs) != 3:
+            return False
+        if not torch.is_grad_enabled():
+            return True
+        needs = any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters())
+        return not needs
+
+    def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor] = None,
+                start: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``start`` (optional, [B] int64 on the device) overrides the FPS start draw; by default it is
+        drawn from the CPU generator exactly like the reference (:36)."""
+        _cuda_only(xyz, "SetAbstraction.forward")
+        B, N, C = xyz.shape
+        fused = self._fused_ok(xyz, points)
+        cout = self.mlp_convs[-1].out_channels
+
+        if self.group_all:
+            new_xyz = torch.zeros(B, 1, 3, device=xyz.device)  # :82
+            if fused:
+                ws, scs, shs = self._folded()
+                new_points = ops.sa_mlp_max(xyz, points, None, None, ws, scs, shs, self.mlp_precision)[:, :cout]
+                return new_xyz, new_points.squeeze(-1)
+            if points is not None:
+                grouped_points = torch.cat([xyz.view(B, 1, N, 3), points.view(B, 1, N, -1)], dim=-1)
+            else:
+                grouped_points = xyz.view(B, 1, N, 3)
+            new_points = self.apply_mlp(grouped_points)
+            return new_xyz, new_points.squeeze(-1)
+
+        if start is None:
+            farthest = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)  # :36, CPU generator
+        else:
+            farthest = start
+        _, new_xyz = ops.fps(xyz, int(self.npoint), farthest)                  # :91-92 (indices + gather)
+        group_idx = query_ball_point(self.radius, self.nsample, xyz, new_xyz)  # :93
+        if fused:
+            ws, scs, shs = self._folded()
+            new_points = ops.sa_mlp_max(xyz, points, new_xyz, group_idx, ws, scs, shs, self.mlp_precision)[:, :cout]
+            return new_xyz, new_points
+        new_points = ops.group(xyz, points, new_xyz, group_idx)                # :94-101
+        new_points = self.apply_mlp(new_points)
+        return new_xyz, new_points
+
+    def apply_mlp(self, points):
+        """models/pointnet2_encoder.py:106-112.  points [B,S,K,C] -> [B,C_out,S]."""
+        if self._fused_ok(points) and points.is_cuda:
+            # a pre-grouped tensor: run it as B*S clouds of K points, one group each (group_all form)
+            B, S, K, C = points.shape
+            ws, scs, shs = self._folded()
+            flat = points.reshape(B * S, K, C)
+            xyz = flat[..., :3].contiguous()
+            feats = flat[..., 3:].contiguous() if C > 3 else None
+            out = ops.sa_mlp_max(xyz, feats, None, None, ws, scs, shs, self.mlp_precision)
+            return out[:, :self.mlp_convs[-1].out_channels, 0].reshape(B, S, -1).permute(0, 2, 1)
+        points = points.permute(0, 3, 1, 2)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            points = F.relu(bn(conv(points)))
+        return torch.max(points, 3)[0]
+
+
+class PointNet2Encoder(nn.Module):
+    """models/pointnet2_encoder.py:114-131.  xyz [B,N,3] -> [B,feature_dim]; ``input_channels`` is
+    accepted and ignored, as in the reference."""
+
+    def __init__(self, input_channels: int = 3, feature_dim: int = 512, mlp_precision: int = 0):
+        super().__init__()
+        self.sa1 = SetAbstraction(512, 0.2, 32, in_channel=0, mlp=[64, 64, 128])
+        self.sa2 = SetAbstraction(128, 0.4, 64, in_channel=128, mlp=[128, 128, 256])
+        self.sa3 = SetAbstraction(npoint=None, radius=None, nsample=None,
+                                  in_channel=256, mlp=[256, 512, feature_dim], group_all=True)
+        self.set_mlp_precision(mlp_precision)
+
+    def set_mlp_precision(self, precision: int) -> "PointNet2Encoder":
+        """0 = fp32 CUDA cores (parity within rtol 1e-4), 1 = bf16 tcgen05 tensor cores (rtol 2e-2)."""
+        for sa in (self.sa1, self.sa2, self.sa3):
+            sa.mlp_precision = int(precision)
+        return self
+
+    def forward(self, xyz: torch.Tensor, starts: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+        """``starts`` (optional) = the FPS start indices of sa1 / sa2 as device tensors; used by
+        ``runtime.GraphedEncoder`` to keep the CPU RNG draws outside a captured CUDA graph."""
+        B, N, C = xyz.shape
+        points = None
+        s1, s2 = starts if starts is not None else (None, None)
+        l1_xyz, l1_points = self.sa1(xyz, points, s1)                           # [B,128,512]
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points.permute(0, 2, 1), s2)    # [B,256,128]
+        _, global_feature = self.sa3(l2_xyz, l2_points.permute(0, 2, 1))        # [B,feature_dim]
+        return global_feature.view(B, -1)

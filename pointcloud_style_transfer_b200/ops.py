@@ -1,0 +1,418 @@
+"""torch custom ops ``pcst::*`` over the C ABI of libpcst.so (``include/pcst.h``).
+
+Each op checks its inputs (CUDA, dtype, layout), allocates outputs and workspace with torch, and
+launches the kernel on torch's current CUDA stream through ctypes.  PyTorch is plumbing here
+(device memory, streams, autograd graph); all arithmetic happens in the CUDA kernels.  There is
+no CPU path: CPU tensors raise.
+"""
+
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import Mlp3, check
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pointcloud_style_transfer_b200 ops run on CUDA (B200) tensors only; "
+                               "there is no CPU fallback")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    """fp32 + contiguous (also opts the distance kernels out of autocast)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _i64c(t: Tensor) -> Tensor:
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# Launch accounting and optional per-op CUDA-event timing (used by bench.py for `gpu_launches` and the
+# roofline's live kernel durations).  KERNELS_PER_CALL counts __global__ launches (memsets excluded).
+KERNELS_PER_CALL = {"pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
+                    "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
+                    "pcst_sa_mlp_max_f32": 3, "pcst_nn_min_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
+                    "pcst_knn_interpolate_f32": 1}
+launch_count = 0
+_event_log = None  # None = off; else list of (name, start_event, end_event)
+
+
+def start_event_log() -> None:
+    global _event_log
+    _event_log = []
+
+
+def stop_event_log():
+    """-> {c_symbol: [ms, ...]} (synchronises the device)."""
+    global _event_log
+    log, _event_log = _event_log or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in log:
+        out.setdefault(name, []).append(a.elapsed_time(b))
+    return out
+
+
+def _call(name: str, *args) -> None:
+    global launch_count
+    fn = getattr(_lib.load(), name)
+    if _event_log is None:
+        check(fn(*args))
+    else:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(fn(*args))
+        b.record()
+        _event_log.append((name, a, b))
+    launch_count += KERNELS_PER_CALL[name]
+
+
+# ------------------------------------------------------------------------------------------ FPS
+
+
+@torch.library.custom_op("pcst::fps", mutates_args=(), device_types="cuda")
+def fps(xyz: Tensor, npoint: int, start: Tensor) -> Tuple[Tensor, Tensor]:
+    """xyz [B,N,3] fp32, start [B] int64 -> (idx [B,npoint] int64, new_xyz [B,npoint,3])."""
+    lib = _lib.load()
+    _need_cuda(xyz, start)
+    xyz, start = _f32c(xyz), _i64c(start)
+    B, N, _ = xyz.shape
+    idx = torch.empty(B, npoint, dtype=torch.int64, device=xyz.device)
+    new_xyz = torch.empty(B, npoint, 3, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        nb = lib.pcst_fps_workspace_bytes(B, N, npoint)
+        ws = _workspace(nb, xyz.device)
+        _call("pcst_fps_f32", _p(xyz), B, N, npoint, _p(start), _p(idx), _p(new_xyz), _p(ws), ws.numel(), _stream())
+    return idx, new_xyz
+
+
+@fps.register_fake
+def _(xyz, npoint, start):
+    B = xyz.shape[0]
+    return xyz.new_empty(B, npoint, dtype=torch.int64), xyz.new_empty(B, npoint, 3, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------- ball query
+
+
+@torch.library.custom_op("pcst::ball_query", mutates_args=(), device_types="cuda")
+def ball_query(xyz: Tensor, new_xyz: Tensor, radius_sq: float, nsample: int) -> Tensor:
+    """xyz [B,N,3], new_xyz [B,S,3], radius_sq = fp32(radius**2) -> idx [B,S,nsample] int64."""
+    lib = _lib.load()
+    _need_cuda(xyz, new_xyz)
+    xyz, new_xyz = _f32c(xyz), _f32c(new_xyz)
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty(B, S, nsample, dtype=torch.int64, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        ws = _workspace(lib.pcst_ball_query_workspace_bytes(B, N, S), xyz.device)
+        _call("pcst_ball_query_f32", _p(xyz), _p(new_xyz), B, N, S, ctypes.c_float(radius_sq), nsample, _p(out),
+                                      _p(ws), ws.numel(), _stream())
+    return out
+
+
+@ball_query.register_fake
+def _(xyz, new_xyz, radius_sq, nsample):
+    return xyz.new_empty(xyz.shape[0], new_xyz.shape[1], nsample, dtype=torch.int64)
+
+
+@torch.library.custom_op("pcst::square_distance", mutates_args=(), device_types="cuda")
+def square_distance(src: Tensor, dst: Tensor) -> Tensor:
+    lib = _lib.load()
+    _need_cuda(src, dst)
+    src, dst = _f32c(src), _f32c(dst)
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    out = torch.empty(B, N, M, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _call("pcst_square_distance_f32", _p(src), _p(dst), B, N, M, _p(out), _stream())
+    return out
+
+
+@square_distance.register_fake
+def _(src, dst):
+    return src.new_empty(src.shape[0], src.shape[1], dst.shape[1], dtype=torch.float32)
+
+
+# ---------------------------------------------------------------------------------- index_points
+
+
+@torch.library.custom_op("pcst::index_points", mutates_args=(), device_types="cuda")
+def index_points(points: Tensor, idx: Tensor) -> Tensor:
+    """points [B,N,C] fp32, idx [B,...] int64 (clamped) -> [B,...,C]."""
+    lib = _lib.load()
+    _need_cuda(points, idx)
+    points, idx = _f32c(points), _i64c(idx)
+    B, N, C = points.shape
+    S = idx.numel() // B
+    out = torch.empty(*idx.shape, C, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _call("pcst_index_points_f32", _p(points), _p(idx), B, N, C, S, _p(out), _stream())
+    return out
+
+
+@index_points.register_fake
+def _(points, idx):
+    return points.new_empty(*idx.shape, points.shape[2], dtype=torch.float32)
+
+
+@torch.library.custom_op("pcst::index_points_bwd", mutates_args=(), device_types="cuda")
+def index_points_bwd(grad_out: Tensor, idx: Tensor, N: int) -> Tensor:
+    lib = _lib.load()
+    _need_cuda(grad_out, idx)
+    grad_out, idx = _f32c(grad_out), _i64c(idx)
+    B = idx.shape[0]
+    C = grad_out.shape[-1]
+    S = idx.numel() // B
+    grad_points = torch.zeros(B, N, C, dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _call("pcst_index_points_bwd_f32", _p(grad_out), _p(idx), B, N, C, S, _p(grad_points), _stream())
+    return grad_points
+
+
+@index_points_bwd.register_fake
+def _(grad_out, idx, N):
+    return grad_out.new_empty(idx.shape[0], N, grad_out.shape[-1], dtype=torch.float32)
+
+
+def _index_points_setup(ctx, inputs, output):
+    points, idx = inputs
+    ctx.save_for_backward(idx)
+    ctx.N = points.shape[1]
+
+
+def _index_points_backward(ctx, grad):
+    (idx,) = ctx.saved_tensors
+    return index_points_bwd(grad, idx, ctx.N), None
+
+
+index_points.register_autograd(_index_points_backward, setup_context=_index_points_setup)
+
+
+# ----------------------------------------------------------------------------------------- group
+
+
+@torch.library.custom_op("pcst::group", mutates_args=(), device_types="cuda")
+def group(xyz: Tensor, feats: Optional[Tensor], new_xyz: Tensor, idx: Tensor) -> Tensor:
+    """cat([xyz[idx] - new_xyz[:, :, None], feats[idx]], -1) -> [B,S,K,3+D]."""
+    lib = _lib.load()
+    _need_cuda(xyz, feats, new_xyz, idx)
+    xyz, new_xyz, idx = _f32c(xyz), _f32c(new_xyz), _i64c(idx)
+    feats = None if feats is None else _f32c(feats)
+    B, N, _ = xyz.shape
+    _, S, K = idx.shape
+    D = 0 if feats is None else feats.shape[2]
+    out = torch.empty(B, S, K, 3 + D, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _call("pcst_group_f32", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, _p(out), _stream())
+    return out
+
+
+@group.register_fake
+def _(xyz, feats, new_xyz, idx):
+    D = 0 if feats is None else feats.shape[2]
+    return xyz.new_empty(*idx.shape, 3 + D, dtype=torch.float32)
+
+
+def _group_setup(ctx, inputs, output):
+    xyz, feats, new_xyz, idx = inputs
+    ctx.save_for_backward(idx)
+    ctx.N = xyz.shape[1]
+    ctx.has_feats = feats is not None
+
+
+def _group_backward(ctx, grad):
+    (idx,) = ctx.saved_tensors
+    g_xyz = index_points_bwd(grad[..., :3].contiguous(), idx, ctx.N)
+    g_new = -grad[..., :3].sum(dim=2)
+    g_feats = index_points_bwd(grad[..., 3:].contiguous(), idx, ctx.N) if ctx.has_feats else None
+    return g_xyz, g_feats, g_new, None
+
+
+group.register_autograd(_group_backward, setup_context=_group_setup)
+
+
+# ---------------------------------------------------------------------------- SA MLP + max-pool
+
+
+@torch.library.custom_op("pcst::sa_mlp_max", mutates_args=(), device_types="cuda")
+def sa_mlp_max(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], idx: Optional[Tensor],
+               weights: List[Tensor], scales: List[Tensor], shifts: List[Tensor], precision: int) -> Tensor:
+    """Fused grouping gather + 3 x relu(scale * (W x) + shift) + max over each group -> [B,Cout,S].
+
+    ``idx is None`` = group_all (one group holding the whole cloud, no centroid subtraction)."""
+    lib = _lib.load()
+    _need_cuda(xyz, feats, new_xyz, idx, *weights, *scales, *shifts)
+    if len(weights) != 3 or len(scales) != 3 or len(shifts) != 3:
+        raise ValueError("sa_mlp_max: the kernel implements the reference's 3-layer shared MLP")
+    xyz = _f32c(xyz)
+    feats = None if feats is None else _f32c(feats)
+    new_xyz = None if new_xyz is None else _f32c(new_xyz)
+    idx = None if idx is None else _i64c(idx)
+    weights = [_f32c(w.reshape(w.shape[0], -1)) for w in weights]
+    scales = [_f32c(s) for s in scales]
+    shifts = [_f32c(s) for s in shifts]
+    B, N, _ = xyz.shape
+    D = 0 if feats is None else feats.shape[2]
+    if idx is None:
+        S, K = 1, N
+    else:
+        _, S, K = idx.shape
+    cin = 3 + D
+    m = Mlp3()
+    for l in range(3):
+        if weights[l].shape[1] != cin:
+            raise ValueError(f"sa_mlp_max: layer {l} expects Cin={weights[l].shape[1]}, got {cin}")
+        m.w[l], m.scale[l], m.shift[l] = weights[l].data_ptr(), scales[l].data_ptr(), shifts[l].data_ptr()
+        m.cout[l] = weights[l].shape[0]
+        cin = weights[l].shape[0]
+    out = torch.empty(B, cin, S, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        nb = lib.pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, ctypes.byref(m), precision)
+        ws = _workspace(nb, xyz.device)
+        _call("pcst_sa_mlp_max_f32", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, ctypes.byref(m),
+                                      precision, _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
+@sa_mlp_max.register_fake
+def _(xyz, feats, new_xyz, idx, weights, scales, shifts, precision):
+    S = 1 if idx is None else idx.shape[1]
+    return xyz.new_empty(xyz.shape[0], weights[2].shape[0], S, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------- NN-min
+
+
+@torch.library.custom_op("pcst::nn_min", mutates_args=(), device_types="cuda")
+def nn_min(a: Tensor, b: Tensor, form: int, want_arg: bool) -> Tuple[Tensor, Tensor]:
+    """Row minima (and argmins if ``want_arg``) of the pair matrix between a [B,N,3] and b [B,M,3].
+    form 0 = loss (clamped squared, expanded), 1 = cdist rows (a = x1), 2 = cdist columns (a = x2)."""
+    lib = _lib.load()
+    _need_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    rowmin = torch.empty(B, N, dtype=torch.float32, device=a.device)
+    rowarg = torch.empty((B, N) if want_arg else (0,), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        ws = _workspace(lib.pcst_nn_min_workspace_bytes(B, N, M), a.device)
+        _call("pcst_nn_min_f32", _p(a), _p(b), B, N, M, form, _p(rowmin), _p(rowarg) if want_arg else None, _p(ws),
+                                  ws.numel(), _stream())
+    return rowmin, rowarg
+
+
+@nn_min.register_fake
+def _(a, b, form, want_arg):
+    B, N = a.shape[0], a.shape[1]
+    return a.new_empty(B, N, dtype=torch.float32), a.new_empty((B, N) if want_arg else (0,), dtype=torch.int64)
+
+
+@torch.library.custom_op("pcst::chamfer_bwd", mutates_args=(), device_types="cuda")
+def chamfer_bwd(pred: Tensor, target: Tensor, arg_pt: Tensor, arg_tp: Tensor, grad_out: Tensor) -> Tuple[Tensor, Tensor]:
+    lib = _lib.load()
+    _need_cuda(pred, target, arg_pt, arg_tp, grad_out)
+    pred, target, grad_out = _f32c(pred), _f32c(target), _f32c(grad_out)
+    arg_pt, arg_tp = _i64c(arg_pt), _i64c(arg_tp)
+    B, N, _ = pred.shape
+    M = target.shape[1]
+    gp, gt = torch.empty_like(pred), torch.empty_like(target)
+    with torch.cuda.device(pred.device):
+        _call("pcst_chamfer_bwd_f32", _p(pred), _p(target), _p(arg_pt), _p(arg_tp), _p(grad_out), B, N, M, _p(gp),
+                                       _p(gt), _stream())
+    return gp, gt
+
+
+@chamfer_bwd.register_fake
+def _(pred, target, arg_pt, arg_tp, grad_out):
+    return torch.empty_like(pred, dtype=torch.float32), torch.empty_like(target, dtype=torch.float32)
+
+
+class _ChamferLoss(torch.autograd.Function):
+    """chamfer[b] = mean_i min_j D(p_i, t_j) + mean_j min_i D(t_j, p_i) (models/losses.py:61)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        need_grad = pred.requires_grad or target.requires_grad
+        d1, a1 = nn_min(pred, target, 0, need_grad)
+        d2, a2 = nn_min(target, pred, 0, need_grad)
+        if need_grad:
+            ctx.save_for_backward(pred, target, a1, a2)
+        return d1.mean(dim=1) + d2.mean(dim=1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        pred, target, a1, a2 = ctx.saved_tensors
+        gp, gt = chamfer_bwd(pred, target, a1, a2, grad)
+        return gp.to(pred.dtype), gt.to(target.dtype)
+
+
+def chamfer_loss(pred: Tensor, target: Tensor) -> Tensor:
+    _need_cuda(pred, target)
+    return _ChamferLoss.apply(pred, target)
+
+
+# ------------------------------------------------------------------------------------------ kNN
+
+
+@torch.library.custom_op("pcst::knn", mutates_args=(), device_types="cuda")
+def knn(query: Tensor, ref: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """query [B,Q,3], ref [B,R,3] -> (dist [B,Q,k] fp64 ascending, idx [B,Q,k] int64); sklearn order."""
+    lib = _lib.load()
+    _need_cuda(query, ref)
+    query, ref = _f32c(query), _f32c(ref)
+    B, Q, _ = query.shape
+    R = ref.shape[1]
+    idx = torch.empty(B, Q, k, dtype=torch.int64, device=query.device)
+    dist = torch.empty(B, Q, k, dtype=torch.float64, device=query.device)
+    with torch.cuda.device(query.device):
+        ws = _workspace(lib.pcst_knn_workspace_bytes(B, Q, R, k), query.device)
+        _call("pcst_knn_f32", _p(query), _p(ref), B, Q, R, k, _p(idx), _p(dist), _p(ws), ws.numel(), _stream())
+    return dist, idx
+
+
+@knn.register_fake
+def _(query, ref, k):
+    B, Q = query.shape[0], query.shape[1]
+    return query.new_empty(B, Q, k, dtype=torch.float64), query.new_empty(B, Q, k, dtype=torch.int64)
+
+
+@torch.library.custom_op("pcst::knn_interpolate", mutates_args=(), device_types="cuda")
+def knn_interpolate(feat: Tensor, idx: Tensor, dist: Tensor) -> Tensor:
+    """feat [B,R,C] fp32, idx/dist [B,Q,k] -> [B,Q,C] inverse-distance weighted (fp64 weights)."""
+    lib = _lib.load()
+    _need_cuda(feat, idx, dist)
+    feat, idx = _f32c(feat), _i64c(idx)
+    dist = dist.double().contiguous()
+    B, R, C = feat.shape
+    _, Q, k = idx.shape
+    out = torch.empty(B, Q, C, dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _call("pcst_knn_interpolate_f32", _p(feat), _p(idx), _p(dist), B, R, Q, k, C, _p(out), _stream())
+    return out
+
+
+@knn_interpolate.register_fake
+def _(feat, idx, dist):
+    return feat.new_empty(feat.shape[0], idx.shape[1], feat.shape[2], dtype=torch.float32)

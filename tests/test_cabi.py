@@ -1,0 +1,87 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/pcst.h declares; argument
+validation paths that need no GPU return the documented status codes."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pointcloud_style_transfer_b200 import _lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(REPO, "include", "pcst.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcst_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pointcloud_style_transfer_b200.build import build
+
+    build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/pcst.h but not exported by libpcst.so"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes prototypes and include/pcst.h disagree"
+
+
+def test_version_and_error_string(lib):
+    assert lib.pcst_version().decode().startswith("pcst ")
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_invalid_arguments_return_status_not_crash(lib):
+    null = ctypes.c_void_p(0)
+    assert lib.pcst_fps_f32(null, 1, 16, 4, null, null, null, null, 0, null) == -1
+    assert "null" in _lib.last_error()
+    assert lib.pcst_ball_query_f32(null, null, 1, 16, 4, ctypes.c_float(0.1), 4, null, null, 0, null) == -1
+    assert lib.pcst_nn_min_f32(null, null, 1, 16, 16, 0, null, null, null, 0, null) == -1
+    assert lib.pcst_knn_f32(null, null, 1, 4, 4, 2, null, null, null, 0, null) == -1
+    one = ctypes.c_void_p(256)  # never dereferenced: the size checks fail first
+    assert lib.pcst_nn_min_f32(one, one, 1, 0, 16, 0, one, null, null, 0, null) == -1
+    assert lib.pcst_nn_min_f32(one, one, 1, 16, 16, 7, one, null, null, 0, null) == -1
+    assert lib.pcst_ball_query_f32(one, one, 1, 16, 4, ctypes.c_float(0.1), 17, one, null, 0, null) == -1  # nsample > N
+    assert lib.pcst_knn_f32(one, one, 1, 4, 4, 17, one, one, null, 0, null) == -1
+    # workspace too small -> PCST_ERR_WORKSPACE
+    assert lib.pcst_nn_min_f32(one, one, 1, 16, 16, 0, one, null, null, 0, null) == -4
+    with pytest.raises(_lib.PcstError):
+        _lib.check(-4)
+
+
+def test_workspace_queries(lib):
+    assert lib.pcst_nn_min_workspace_bytes(1, 120000, 120000) >= 2 * 120000 * 16
+    assert lib.pcst_ball_query_workspace_bytes(1, 120000, 512) >= 120000 * 16
+    assert lib.pcst_fps_workspace_bytes(1, 120000, 512) == 0          # register-resident
+    assert lib.pcst_fps_workspace_bytes(1, 500000, 512) >= 500000 * 4  # streaming fallback keeps distances in HBM
+    assert lib.pcst_nn_min_workspace_bytes(0, 1, 1) == 0
+
+
+def test_tuning_knobs(lib):
+    _lib.set_tuning("nn_min.splits", 3)
+    assert _lib.get_tuning("nn_min.splits") == 3
+    _lib.set_tuning("nn_min.splits", 0)
+    with pytest.raises(_lib.PcstError):
+        _lib.set_tuning("no.such.knob", 1)
+
+
+def test_cpu_tensors_raise_loudly():
+    import torch
+
+    from pointcloud_style_transfer_b200.models.pointnet2_encoder import farthest_point_sample, query_ball_point
+    from pointcloud_style_transfer_b200.models.losses import chamfer_distance_chunked_optimized
+
+    x = torch.rand(1, 64, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        farthest_point_sample(x, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        query_ball_point(0.2, 8, x, x[:, :4])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        chamfer_distance_chunked_optimized(x, x)

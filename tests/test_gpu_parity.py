@@ -1,0 +1,443 @@
+"""GPU: the CUDA path (through the public drop-in API -> pcst::* custom ops -> C ABI) against the CPU
+oracle on the same seeded inputs and against the committed golden vectors produced by the reference.
+
+Bars: indices (FPS, ball query, kNN) and loss-form per-point minima BIT-EXACT; cdist-form distances
+within 1 ulp (torch's CPU sqrt is not correctly rounded); fp32 MLP features rtol 1e-4 / atol 1e-5;
+Chamfer scalars rtol 1e-5; interpolated values rtol 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from pointcloud_style_transfer_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from pointcloud_style_transfer_b200 import ops
+    from pointcloud_style_transfer_b200.evaluation.metrics import PointCloudMetrics
+    from pointcloud_style_transfer_b200.models import diffusion_model, losses, pointnet2_encoder
+
+    class A:
+        pass
+
+    a = A()
+    a.ops, a.enc, a.losses, a.dm, a.Metrics = ops, pointnet2_encoder, losses, diffusion_model, PointCloudMetrics
+    return a
+
+
+# ------------------------------------------------------------------------------------------ FPS
+
+
+def run_fps(api, dev, x, npoint, start):
+    idx, new_xyz = api.ops.fps(torch.as_tensor(x).to(dev), npoint, torch.as_tensor(start).to(dev))
+    return idx.cpu().numpy(), new_xyz.cpu().numpy()
+
+
+@pytest.mark.parametrize("B,N,npoint", [(2, 4096, 512), (1, 512, 128), (3, 1000, 100), (2, 16384, 512),
+                                        (1, 33, 33), (1, 8200, 64), (1, 70000, 96)])
+def test_fps_matches_oracle(api, dev, oracle, B, N, npoint):
+    x = S.uniform_cloud(N, B, N).numpy()
+    start = S.fps_start(1, B, N).numpy()
+    idx, new_xyz = run_fps(api, dev, x, npoint, start)
+    ref = oracle.farthest_point_sample(x, npoint, start)
+    assert np.array_equal(idx, ref)
+    assert np.array_equal(new_xyz, oracle.index_points(x, ref))
+
+
+@pytest.mark.parametrize("name", ["lidar", "uniform"])
+def test_fps_120k_golden_and_oracle(api, dev, oracle, golden, name):
+    g = golden("c2_120k_" + name)
+    x = (S.lidar_scan(0) if name == "lidar" else S.uniform_cloud(0, 1, 120000)).numpy()
+    idx, _ = run_fps(api, dev, x, 512, g["start1"])
+    assert np.array_equal(idx, g["fps1"]), "FPS differs from the reference's own output"
+    assert np.array_equal(idx, oracle.farthest_point_sample(x, 512, g["start1"]))
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+def test_fps_every_cluster_size(api, dev, oracle, cluster):
+    from pointcloud_style_transfer_b200 import _lib
+
+    N = 8000
+    x = S.uniform_cloud(3, 2, N).numpy()
+    start = S.fps_start(2, 2, N).numpy()
+    _lib.set_tuning("fps.cluster", cluster)
+    try:
+        idx, _ = run_fps(api, dev, x, 200, start)
+    finally:
+        _lib.set_tuning("fps.cluster", 0)
+    assert np.array_equal(idx, oracle.farthest_point_sample(x, 200, start))
+
+
+def test_fps_streaming_fallback_large_cloud(api, dev, oracle):
+    N = 150000  # > 16 CTAs x 8192 register-resident points
+    x = S.uniform_cloud(4, 1, N).numpy()
+    start = np.array([77], np.int64)
+    idx, _ = run_fps(api, dev, x, 48, start)
+    assert np.array_equal(idx, oracle.farthest_point_sample(x, 48, start))
+
+
+def test_fps_ties_lattice_and_degenerate(api, dev, golden):
+    g = golden("lattice")
+    idx, _ = run_fps(api, dev, g["x"], 256, g["start"])
+    assert np.array_equal(idx, g["fps"])
+    e = golden("edge_fps")
+    idx, _ = run_fps(api, dev, e["x"], 100, e["start"])
+    assert np.array_equal(idx, e["fps"])           # npoint > distinct positions: zero-distance ties -> index 0
+    idx, _ = run_fps(api, dev, np.zeros((1, 50, 3), np.float32), 10, e["same_start"])
+    assert np.array_equal(idx, e["same_fps"])
+
+
+def test_farthest_point_sample_consumes_cpu_rng_like_reference(api, dev, golden):
+    g = golden("c1_encoder")
+    torch.manual_seed(1234)
+    idx = api.enc.farthest_point_sample(torch.from_numpy(g["x"]).to(dev), 512)
+    assert idx.dtype == torch.int64 and idx.shape == (2, 512)
+    assert np.array_equal(idx.cpu().numpy(), g["fps1"])
+
+
+# ----------------------------------------------------------------------------------- ball query
+
+
+@pytest.mark.parametrize("B,N,S_,radius,nsample", [(2, 4096, 512, 0.2, 32), (2, 512, 128, 0.4, 64),
+                                                   (1, 3000, 77, 0.05, 16), (1, 1024, 5, 3.0, 1024),
+                                                   (1, 1025, 9, 0.3, 8)])
+def test_ball_query_matches_oracle(api, dev, oracle, B, N, S_, radius, nsample):
+    x = S.uniform_cloud(N + 1, B, N)
+    q = x[:, torch.randperm(N, generator=torch.Generator().manual_seed(0))[:S_]].contiguous()
+    out = api.enc.query_ball_point(radius, nsample, x.to(dev), q.to(dev)).cpu().numpy()
+    assert np.array_equal(out, oracle.query_ball_point(radius, nsample, x.numpy(), q.numpy()))
+
+
+@pytest.mark.parametrize("name", ["lidar", "uniform"])
+def test_ball_query_120k_golden(api, dev, oracle, golden, name):
+    g = golden("c2_120k_" + name)
+    x = S.lidar_scan(0) if name == "lidar" else S.uniform_cloud(0, 1, 120000)
+    c1 = torch.from_numpy(oracle.index_points(x.numpy(), g["fps1"].astype(np.int64)))
+    out = api.enc.query_ball_point(0.2, 32, x.to(dev), c1.to(dev)).cpu().numpy()
+    assert np.array_equal(out, g["group1"]), "ball query differs from the reference's own output"
+    c2 = torch.from_numpy(oracle.index_points(c1.numpy(), g["fps2"].astype(np.int64)))
+    out2 = api.enc.query_ball_point(0.4, 64, c1.to(dev), c2.to(dev)).cpu().numpy()
+    assert np.array_equal(out2, g["group2"])
+
+
+def test_ball_query_edges(api, dev, golden):
+    g = golden("edge_ball_query")
+    x, q = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["q"]).to(dev)
+    tiny = api.enc.query_ball_point(float(g["r_tiny"]), 8, x, q).cpu().numpy()
+    assert np.array_equal(tiny, g["tiny"])
+    assert (tiny[0, 5:] == 300).all()  # empty balls -> sentinel N
+    huge = api.enc.query_ball_point(float(g["r_huge"]), 300, x, q[:, :5].contiguous()).cpu().numpy()
+    assert np.array_equal(huge, g["huge"])
+    with pytest.raises(IndexError):
+        api.enc.query_ball_point(5.0, 400, x, q)
+    lat = golden("lattice")
+    xq = torch.from_numpy(lat["x"]).to(dev)
+    nq = api.enc.index_points(xq, torch.from_numpy(lat["fps"].astype(np.int64)).to(dev))
+    assert np.array_equal(api.enc.query_ball_point(0.25, 16, xq, nq).cpu().numpy(), lat["group"])
+
+
+def test_square_distance_bit_exact(api, dev, golden, oracle):
+    g = golden("square_distance")
+    out = api.enc.square_distance(torch.from_numpy(g["src"]).to(dev), torch.from_numpy(g["dst"]).to(dev))
+    assert np.array_equal(bits(out.cpu().numpy()), bits(g["out"]))
+    a, b = S.uniform_cloud(1, 1, 300).numpy(), S.uniform_cloud(2, 1, 5000).numpy()
+    out = api.enc.square_distance(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)).cpu().numpy()
+    assert np.array_equal(bits(out), bits(oracle.square_distance(a, b)))
+
+
+# --------------------------------------------------------------------------- gather / grouping
+
+
+def test_index_points_and_group(api, dev, oracle):
+    pts = torch.randn(2, 500, 131, generator=torch.Generator().manual_seed(0))
+    idx = torch.randint(-3, 505, (2, 40, 7), generator=torch.Generator().manual_seed(1))  # out of range: clamped
+    out = api.enc.index_points(pts.to(dev), idx.to(dev)).cpu().numpy()
+    assert np.array_equal(out, oracle.index_points(pts.numpy(), idx.numpy()))
+    idx2 = idx[:, :, 0].contiguous()
+    out2 = api.enc.index_points(pts.to(dev), idx2.to(dev)).cpu().numpy()
+    assert np.array_equal(out2, oracle.index_points(pts.numpy(), idx2.numpy()))
+    xyz = pts[..., :3].contiguous()
+    new_xyz = torch.randn(2, 40, 3, generator=torch.Generator().manual_seed(2))
+    grp = api.ops.group(xyz.to(dev), pts.to(dev), new_xyz.to(dev), idx.to(dev)).cpu().numpy()
+    ref = np.concatenate([oracle.index_points(xyz.numpy(), idx.numpy()) - new_xyz.numpy()[:, :, None, :],
+                          oracle.index_points(pts.numpy(), idx.numpy())], -1)
+    assert np.array_equal(grp, ref)
+
+
+def test_index_points_backward_matches_autograd_of_reference_formula(api, dev):
+    pts = torch.randn(2, 50, 6, generator=torch.Generator().manual_seed(0)).to(dev).requires_grad_(True)
+    idx = torch.randint(0, 50, (2, 30, 4), generator=torch.Generator().manual_seed(1)).to(dev)
+    w = torch.randn(2, 30, 4, 6, generator=torch.Generator().manual_seed(2)).to(dev)
+    (api.enc.index_points(pts, idx) * w).sum().backward()
+    g_ours = pts.grad.clone()
+    pts.grad = None
+    b = torch.arange(2, device=dev).view(2, 1, 1).expand_as(idx)
+    (pts[b, idx, :] * w).sum().backward()  # the reference's advanced-indexing formulation (:25-27)
+    torch.testing.assert_close(g_ours, pts.grad, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------- encoder / MLP
+
+
+def load_encoder(api, golden, dev, precision=0):
+    g = golden("c1_encoder")
+    enc = api.enc.PointNet2Encoder(feature_dim=256, mlp_precision=precision)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    missing, unexpected = enc.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in m for m in missing)
+    return g, enc.eval().to(dev)
+
+
+def test_encoder_c1_against_reference_golden(api, dev, golden):
+    g, enc = load_encoder(api, golden, dev)
+    x = torch.from_numpy(g["x"]).to(dev)
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        l1_xyz, l1_pts = enc.sa1(x, None)
+        l2_xyz, l2_pts = enc.sa2(l1_xyz, l1_pts.permute(0, 2, 1))
+    assert l1_pts.shape == (2, 128, 512) and l2_pts.shape == (2, 256, 128)
+    np.testing.assert_allclose(l1_pts.cpu().numpy(), g["l1_points"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(l2_pts.cpu().numpy(), g["l2_points"], rtol=1e-4, atol=1e-5)
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        feat = enc(x)
+    assert feat.shape == (2, 256)
+    np.testing.assert_allclose(feat.cpu().numpy(), g["feature"], rtol=1e-4, atol=1e-5)
+
+
+def test_encoder_120k_against_oracle(api, dev, oracle, golden):
+    g, enc = load_encoder(api, golden, dev)
+    x = S.lidar_scan(0)
+    torch.manual_seed(7)
+    s1 = torch.randint(0, 120000, (1,), dtype=torch.long).numpy()
+    s2 = torch.randint(0, 512, (1,), dtype=torch.long).numpy()
+    torch.manual_seed(7)
+    with torch.no_grad():
+        feat = enc(x.to(dev)).cpu().numpy()
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    ref = oracle.encoder_forward(x.numpy(), sd, s1, s2)
+    np.testing.assert_allclose(feat, ref["feature"], rtol=1e-4, atol=1e-5)
+
+
+def test_graphed_encoder_equals_eager(api, dev, golden):
+    from pointcloud_style_transfer_b200.runtime import GraphedEncoder
+
+    g, enc = load_encoder(api, golden, dev)
+    genc = GraphedEncoder(enc)
+    x = torch.from_numpy(g["x"]).to(dev)
+    for seed in (1234, 5):
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            eager = enc(x).clone()
+        torch.manual_seed(seed)
+        graphed = genc(x).clone()
+        assert torch.equal(eager, graphed)
+    torch.manual_seed(1234)
+    np.testing.assert_allclose(genc(torch.from_numpy(g["x"]).pin_memory()).cpu().numpy(), g["feature"], rtol=1e-4, atol=1e-5)
+
+
+def test_apply_mlp_odd_channel_count_is_padded(api, dev, oracle):
+    torch.manual_seed(0)
+    sa = api.enc.SetAbstraction(16, 0.5, 8, in_channel=5, mlp=[24, 40, 100]).eval().to(dev)
+    for bn in sa.mlp_bns:
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+    pts = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        out = sa.apply_mlp(pts.to(dev)).cpu().numpy()
+    sd = {k: v.detach().cpu().numpy() for k, v in sa.state_dict().items()}
+    ref = oracle.apply_mlp(pts.numpy(), oracle.layers_from_state_dict(sd, ""))
+    assert out.shape == (2, 100, 16)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_set_abstraction_training_mode_matches_torch_composition(api, dev):
+    """Train mode: our gather ops + torch's conv/bn must equal the reference formulation, including
+    gradients to the parameters and updated BatchNorm running statistics."""
+    torch.manual_seed(3)
+    sa = api.enc.SetAbstraction(32, 0.4, 16, in_channel=4, mlp=[32, 32, 64]).to(dev).train()
+    x = S.uniform_cloud(5, 2, 600).to(dev)
+    f = torch.randn(2, 600, 4, generator=torch.Generator().manual_seed(4)).to(dev).requires_grad_(True)
+    torch.manual_seed(11)
+    new_xyz, out = sa(x, f)
+    out.square().mean().backward()
+    # the same computation written with torch indexing
+    torch.manual_seed(11)
+    import copy
+    sb = copy.deepcopy(sa)
+    for m in sb.mlp_bns:
+        m.reset_running_stats()
+    f2 = f.detach().clone().requires_grad_(True)
+    idx = api.enc.farthest_point_sample(x, 32)
+    nx = x[torch.arange(2, device=dev)[:, None], idx]
+    gi = api.enc.query_ball_point(0.4, 16, x, nx)
+    b = torch.arange(2, device=dev).view(2, 1, 1)
+    grouped = torch.cat([x[b, gi] - nx[:, :, None, :], f2[b, gi]], -1).permute(0, 3, 1, 2)
+    for conv, bn in zip(sb.mlp_convs, sb.mlp_bns):
+        grouped = torch.relu(bn(conv(grouped)))
+    ref = grouped.max(3)[0]
+    for p in sb.parameters():
+        p.grad = None
+    ref.square().mean().backward()
+    torch.testing.assert_close(new_xyz, nx)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(f.grad, f2.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(sa.mlp_bns[0].running_mean, sb.mlp_bns[0].running_mean, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------- Chamfer / NN-min
+
+
+def test_chamfer_c1_golden_bit_exact_minima(api, dev, golden):
+    g = golden("c1_chamfer")
+    p, t = torch.from_numpy(g["pred"]).to(dev), torch.from_numpy(g["target"]).to(dev)
+    d1, _ = api.ops.nn_min(p, t, 0, False)
+    d2, _ = api.ops.nn_min(t, p, 0, False)
+    assert np.array_equal(bits(d1.cpu().numpy()), bits(g["loss_rowmin"]))
+    assert np.array_equal(bits(d2.cpu().numpy()), bits(g["loss_colmin"]))
+    cd = api.losses.chamfer_distance_chunked_optimized(p, t).cpu().numpy()
+    np.testing.assert_allclose(cd, g["chamfer_loss"], rtol=1e-5)
+    cd100 = api.losses.chamfer_distance_chunked_optimized(p, t, 100).cpu().numpy()
+    np.testing.assert_allclose(cd100, g["chamfer_loss_chunk100"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,N,M", [(1, 30000, 30000), (2, 1000, 7777), (1, 1, 5), (3, 1025, 1023)])
+def test_nn_min_loss_form_matches_oracle(api, dev, oracle, B, N, M, variant):
+    from pointcloud_style_transfer_b200 import _lib
+
+    a, b = S.uniform_cloud(10, B, N).numpy(), S.uniform_cloud(20, B, M).numpy()
+    _lib.set_tuning("nn_min.variant", variant)  # 1 = scalar FFMA, 2 = packed fp32x2
+    try:
+        d, _ = api.ops.nn_min(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), 0, False)
+        dv, arg = api.ops.nn_min(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), 0, True)
+    finally:
+        _lib.set_tuning("nn_min.variant", 0)
+    ref, refarg = oracle.nn_min(a, b, 0, want_arg=True)
+    assert np.array_equal(bits(d.cpu().numpy()), bits(ref))
+    assert np.array_equal(bits(dv.cpu().numpy()), bits(ref))
+    assert np.array_equal(arg.cpu().numpy(), refarg)
+
+
+def test_nn_min_120k_rows_subset_and_properties(api, dev, oracle):
+    """Full 120k x 120k on the GPU; the oracle checks a 2048-row subset exactly (every row's minimum
+    over all 120k candidates), plus size-independent properties on the whole result."""
+    a, b = S.lidar_scan(0), S.lidar_scan(1)
+    da, db = a.to(dev), b.to(dev)
+    d1, arg1 = api.ops.nn_min(da, db, 0, True)
+    d1n, _ = api.ops.nn_min(da, db, 0, False)
+    assert torch.equal(d1, d1n)
+    rows = np.sort(np.random.RandomState(0).permutation(120000)[:2048])
+    ref, refarg = oracle.nn_min(a.numpy()[:, rows], b.numpy(), 0, want_arg=True)
+    assert np.array_equal(bits(d1.cpu().numpy()[:, rows]), bits(ref))
+    assert np.array_equal(arg1.cpu().numpy()[:, rows], refarg)
+    # properties: self-distance is 0 with argmin = first duplicate; min is attained at the argmin
+    d0, a0 = api.ops.nn_min(da, da, 0, True)
+    assert float(d0.max()) <= 1e-6
+    pair = torch.gather(db[0], 0, arg1[0][:, None].expand(-1, 3))
+    direct = ((da[0] - pair) ** 2).sum(-1)
+    torch.testing.assert_close(d1[0], direct, rtol=1e-3, atol=2e-6)
+    # and a subset of rows evaluated alone gives the same minima (tiling / split independence)
+    sub, _ = api.ops.nn_min(da[:, 5000:6000].contiguous(), db, 0, False)
+    assert torch.equal(sub, d1[:, 5000:6000])
+
+
+def test_nn_min_lattice_order_independent(api, dev, golden):
+    g = golden("lattice")
+    x, y = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)
+    d1, _ = api.ops.nn_min(x, y, 0, False)
+    d2, _ = api.ops.nn_min(y, x, 0, False)
+    assert np.array_equal(bits(d1.cpu().numpy()), bits(g["loss_rowmin"]))
+    assert np.array_equal(bits(d2.cpu().numpy()), bits(g["loss_colmin"]))
+    np.testing.assert_allclose(api.losses.chamfer_distance_chunked_optimized(x, y).cpu().numpy(), g["chamfer_loss"], rtol=1e-6)
+
+
+def test_metrics_chamfer_hausdorff(api, dev, golden, oracle):
+    g = golden("c1_chamfer")
+    p, t = torch.from_numpy(g["pred"]).to(dev), torch.from_numpy(g["target"]).to(dev)
+    M = api.Metrics("cuda")
+    d1, _ = api.ops.nn_min(p, t, 1, False)
+    d2, _ = api.ops.nn_min(t, p, 2, False)
+    # bit-exact with the oracle (correctly rounded sqrt), 1 ulp from torch's vectorised CPU sqrt
+    assert np.array_equal(bits(d1.cpu().numpy()), bits(oracle.nn_min(g["pred"], g["target"], 1)))
+    assert np.array_equal(bits(d2.cpu().numpy()), bits(oracle.nn_min(g["target"], g["pred"], 2)))
+    np.testing.assert_allclose(d1.cpu().numpy(), g["metric_rowmin"], rtol=1.2e-7)
+    np.testing.assert_allclose(d2.cpu().numpy(), g["metric_colmin"], rtol=1.2e-7)
+    np.testing.assert_allclose(M.chamfer_distance(p, t).cpu().numpy(), g["metric_cd"], rtol=1e-6)
+    np.testing.assert_allclose(M.chamfer_distance(p, t, bidirectional=False).cpu().numpy(), g["metric_cd_oneway"], rtol=1e-6)
+    np.testing.assert_allclose(M.hausdorff_distance(p, t).cpu().numpy(), g["metric_hausdorff"], rtol=1.2e-7)
+
+
+def test_chamfer_backward_matches_autograd_of_reference_formula(api, dev):
+    p = S.uniform_cloud(1, 2, 700).to(dev).requires_grad_(True)
+    t = S.uniform_cloud(2, 2, 900).to(dev).requires_grad_(True)
+    w = torch.tensor([0.3, 1.7], device=dev)
+    (api.losses.chamfer_distance_chunked_optimized(p, t) * w).sum().backward()
+    gp, gt = p.grad.clone(), t.grad.clone()
+    p.grad = t.grad = None
+    psq, tsq = (p ** 2).sum(-1, keepdim=True), (t ** 2).sum(-1, keepdim=True).transpose(1, 2)
+    D = torch.clamp(psq + tsq + (-2 * torch.bmm(p, t.transpose(1, 2))), min=0)  # losses.py:36-39
+    ((D.min(2)[0].mean(1) + D.min(1)[0].mean(1)) * w).sum().backward()
+    torch.testing.assert_close(gp, p.grad, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gt, t.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_diffusion_loss_call_site(api, dev, oracle):
+    L = api.losses.DiffusionLoss(noise_weight=1.0, chamfer_weight=0.1)
+    pn, an = torch.randn(2, 300, 3, device=dev), torch.randn(2, 300, 3, device=dev)
+    p, t = S.uniform_cloud(1, 2, 300).to(dev), S.uniform_cloud(2, 2, 300).to(dev)
+    total, d = L(pn, an, p, t)
+    cd = oracle.chamfer_distance_chunked_optimized(p.cpu().numpy(), t.cpu().numpy()).mean()
+    assert abs(d["chamfer_loss"] - cd) < 1e-6 * max(1, cd)
+    assert abs(d["total_loss"] - (d["noise_loss"] + 0.1 * d["chamfer_loss"])) < 1e-5
+    assert set(L(pn, an)[1]) == {"noise_loss", "total_loss"}
+
+
+# ------------------------------------------------------------------------------- kNN / upsample
+
+
+@pytest.mark.parametrize("k", [1, 3, 9, 16])
+def test_knn_matches_oracle(api, dev, oracle, k):
+    q, r = S.uniform_cloud(1, 2, 1500).numpy(), S.uniform_cloud(2, 2, 4000).numpy()
+    dist, idx = api.ops.knn(torch.from_numpy(q).to(dev), torch.from_numpy(r).to(dev), k)
+    rd, ri = oracle.knn(q, r, k)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert np.array_equal(dist.cpu().numpy(), rd)  # fp64, same operation order -> identical
+
+
+def test_upsample_knn_golden(api, dev, golden, oracle):
+    g = golden("upsample_knn")
+    hp = api.dm.HierarchicalProcessor(6000, 1500)
+    out = hp.upsample_knn(torch.from_numpy(g["coarse"]).to(dev), torch.from_numpy(g["original"]).to(dev),
+                          torch.from_numpy(g["indices"]).to(dev))
+    assert out.dtype == torch.float32 and out.shape == (2, 6000, 3)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-6, atol=1e-7)
+    # duplicated and out-of-range coarse indices (last write wins; indices >= N dropped)
+    idx = g["indices"].copy()
+    idx[:, 10] = idx[:, 3]
+    idx[:, 20] = 6000
+    out2 = hp.upsample_knn(torch.from_numpy(g["coarse"]).to(dev), torch.from_numpy(g["original"]).to(dev),
+                           torch.from_numpy(idx).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(out2, oracle.upsample_knn(g["coarse"], g["original"], idx), rtol=1e-6, atol=1e-7)
+
+
+def test_coverage_uniformity_golden(api, dev, golden):
+    g = golden("upsample_knn")
+    M = api.Metrics("cuda")
+    p, t = torch.from_numpy(g["pred"]).to(dev), torch.from_numpy(g["target"]).to(dev)
+    assert abs(M.coverage_score(p, t, 0.05) - float(g["coverage_005"])) < 1e-12
+    assert abs(M.coverage_score(p, t, 0.01) - float(g["coverage_001"])) < 1e-12
+    assert abs(M.uniformity_score(p, 8) - float(g["uniformity_8"])) < 1e-9
+    assert abs(M.uniformity_score(t, 4) - float(g["uniformity_4"])) < 1e-9
