@@ -31,7 +31,6 @@ static std::map<std::string, int>& tune_map() {
         {"nn_min.variant", 0},        // 0 = auto
         {"nn_min.splits", 0},         // 0 = auto (candidate-range splits per row tile)
         {"fps.cluster", 0},           // 0 = auto (CTAs per cloud)
-        {"ball_query.warps", 0},      // 0 = auto (queries per CTA)
         {"sa_mlp.variant", 0},
     };
     return m;

@@ -223,7 +223,7 @@ template <int P>
 static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoint, const int64_t* start,
                       int64_t* out, float* new_xyz, float* dist_ws, cudaStream_t stream) {
     auto kern = fps_kernel<P>;
-    if (p.smem > 48 * 1024)
+    if (p.smem > 32 * 1024)  // dynamic + static (FpsShared) must stay under the opt-in limit, not the 48 KiB default
         PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     if (p.C > 8) PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};

@@ -50,7 +50,7 @@ def _workspace(nbytes: int, device) -> Tensor:
 
 # Launch accounting and optional per-op CUDA-event timing (used by bench.py for `gpu_launches` and the
 # roofline's live kernel durations).  KERNELS_PER_CALL counts __global__ launches (memsets excluded).
-KERNELS_PER_CALL = {"pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
+KERNELS_PER_CALL = {"pcst_fps_f32": 1, "pcst_ball_query_f32": 3, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
                     "pcst_sa_mlp_max_f32": 3, "pcst_nn_min_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
                     "pcst_knn_interpolate_f32": 1}

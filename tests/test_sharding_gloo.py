@@ -1,0 +1,83 @@
+"""CPU, world_size 2, gloo: the host-side sharding logic of pointcloud_style_transfer_b200.distributed
+(ragged all-gather, query-sharded Chamfer, scan-sharded encoding) with the CPU oracle injected as the
+local compute.  The CUDA kernels are not involved here; the same functions run on NCCL in production."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pointcloud_style_transfer_b200 import distributed as D
+from pointcloud_style_transfer_b200 import synthetic as S
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_nn_min(a, b, form):
+    from oracle import ref_oracle as O
+    return torch.from_numpy(O.nn_min(a.numpy(), b.numpy(), form))
+
+
+class _ToyEncoder(torch.nn.Module):
+    def forward(self, x):  # [S,N,3] -> [S,4]: any per-scan function will do for the plumbing test
+        return torch.cat([x.mean(dim=1), x.abs().amax(dim=(1, 2))[:, None]], dim=1)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pred, target = S.uniform_cloud(0, 2, 1001), S.uniform_cloud(100, 2, 777)  # ragged over 2 ranks
+        lo, hi = D.slice_of_rank(1001, world, rank)
+        lo2, hi2 = D.slice_of_rank(777, world, rank)
+        g = D.all_gather_ragged(pred[:, lo:hi].contiguous())
+        ok_gather = torch.equal(g, pred)
+        cd = D.chamfer_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), nn_min_fn=_oracle_nn_min)
+        cdm = D.chamfer_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), nn_min_fn=_oracle_nn_min, form=1)
+        scans = S.uniform_cloud(5, 5, 64)
+        feats = D.encode_scans_sharded(_ToyEncoder(), scans)
+        q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_query_sharded_chamfer_and_scan_sharding_world2(oracle):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pred, target = S.uniform_cloud(0, 2, 1001), S.uniform_cloud(100, 2, 777)
+    ref = oracle.chamfer_distance_chunked_optimized(pred.numpy(), target.numpy())
+    refm = oracle.metrics_chamfer_distance(pred.numpy(), target.numpy())
+    scans = S.uniform_cloud(5, 5, 64)
+    ref_feats = _ToyEncoder()(scans).numpy()
+    for rank, ok_gather, cd, cdm, feats in res:
+        assert ok_gather
+        np.testing.assert_allclose(cd, ref, rtol=1e-6)
+        np.testing.assert_allclose(cdm, refm, rtol=1e-6)
+        np.testing.assert_array_equal(feats, ref_feats)
+
+
+def test_partition_helpers():
+    assert D.scans_of_rank(8, 8, 3) == [3]
+    assert D.scans_of_rank(5, 2, 1) == [1, 3]
+    covered = []
+    for r in range(8):
+        lo, hi = D.slice_of_rank(120001, 8, r)
+        covered += list(range(lo, hi))
+    assert covered == list(range(120001))
+    assert D.slice_of_rank(3, 8, 7) == (3, 3)  # more ranks than points: empty slice

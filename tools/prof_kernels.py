@@ -1,0 +1,59 @@
+"""Runs each hot kernel a few times on the BASELINE shapes (for `ncu` captures and quick CUDA-event timings).
+
+    python tools/prof_kernels.py [fps] [ball] [nn] [mlp] [enc] [knn]
+"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pointcloud_style_transfer_b200 import ops, synthetic as S  # noqa: E402
+from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder  # noqa: E402
+
+which = set(sys.argv[1:]) or {"fps", "ball", "nn", "mlp", "enc", "knn"}
+dev = torch.device("cuda:0")
+x = S.lidar_scan(0).to(dev)
+y = S.lidar_scan(100).to(dev)
+start = torch.tensor([1234], device=dev)
+
+
+def timeit(name, fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    print(f"{name}: {a.elapsed_time(b) / reps * 1e3:.1f} us", flush=True)
+
+
+if "fps" in which:
+    timeit("fps 120k->512", lambda: ops.fps(x, 512, start))
+    x16 = S.uniform_cloud(0, 4, 16384).to(dev)
+    st4 = torch.zeros(4, dtype=torch.long, device=dev)
+    timeit("fps 4x16384->512", lambda: ops.fps(x16, 512, st4))
+    x512 = S.uniform_cloud(0, 1, 512).to(dev)
+    timeit("fps 512->128", lambda: ops.fps(x512, 128, start * 0))
+if "ball" in which:
+    _, c1 = ops.fps(x, 512, start)
+    timeit("ball_query 512x120k r=0.2 ns=32", lambda: ops.ball_query(x, c1, 0.04, 32))
+if "nn" in which:
+    timeit("nn_min 120k x 120k form0", lambda: ops.nn_min(x, y, 0, False), reps=3)
+    timeit("nn_min 120k x 120k form0 +arg", lambda: ops.nn_min(x, y, 0, True), reps=3)
+    timeit("nn_min 120k x 120k form1", lambda: ops.nn_min(x, y, 1, False), reps=3)
+if "enc" in which or "mlp" in which:
+    torch.manual_seed(42)
+    for prec in (0, 1):
+        enc = PointNet2Encoder(feature_dim=256, mlp_precision=prec).eval().to(dev)
+        try:
+            with torch.no_grad():
+                timeit(f"encoder eager precision={prec}", lambda: enc(x))
+        except Exception as e:  # the tensor-core path may not be built yet
+            print(f"encoder precision={prec}: {type(e).__name__}: {str(e)[:120]}")
+if "knn" in which:
+    q, r = S.uniform_cloud(1, 1, 90000).to(dev), S.uniform_cloud(2, 1, 30000).to(dev)
+    timeit("knn 90k x 30k k=3", lambda: ops.knn(q, r, 3), reps=2)
