@@ -147,6 +147,7 @@ mlp_layer_kernel(const LayerArgs a) {
 int sa_mlp_max_tc(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
                   int K, int D, const pcst_mlp3_t* mlp, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t sa_mlp_max_tc_workspace(int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp);
+bool sa_mlp_max_tc_supported(int D, const pcst_mlp3_t* mlp);
 
 }  // namespace pcst
 
@@ -164,7 +165,9 @@ static int check_mlp(const pcst_mlp3_t* mlp) {
 extern "C" size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp,
                                                   int precision) {
     if (B <= 0 || N <= 0 || S <= 0 || K <= 0 || D < 0 || !check_mlp(mlp)) return 0;
-    if (precision == 1) return sa_mlp_max_tc_workspace(B, N, S, K, D, mlp);
+    // stages whose layers do not fit the tensor-core kernel (Cout > 256: the tiny group_all stage) run
+    // on the fp32 path, which is the more precise of the two
+    if (precision == 1 && sa_mlp_max_tc_supported(D, mlp)) return sa_mlp_max_tc_workspace(B, N, S, K, D, mlp);
     const size_t rows = (size_t)B * S * K;
     return align_up(rows * mlp->cout[0] * sizeof(float), 256) + align_up(rows * mlp->cout[1] * sizeof(float), 256);
 }
@@ -185,7 +188,8 @@ extern "C" int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const f
         set_error("pcst_sa_mlp_max_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need);
         return PCST_ERR_WORKSPACE;
     }
-    if (precision == 1) return sa_mlp_max_tc(xyz, feats, new_xyz, idx, B, N, S, K, D, mlp, out, ws, ws_bytes, stream);
+    if (precision == 1 && sa_mlp_max_tc_supported(D, mlp))
+        return sa_mlp_max_tc(xyz, feats, new_xyz, idx, B, N, S, K, D, mlp, out, ws, ws_bytes, stream);
 
     const size_t rows_sz = (size_t)B * S * K;
     PCST_CHECK_ARG(rows_sz < (1u << 30), "B*S*K too large");

@@ -231,6 +231,42 @@ def test_encoder_120k_against_oracle(api, dev, oracle, golden):
     np.testing.assert_allclose(feat, ref["feature"], rtol=1e-4, atol=1e-5)
 
 
+def test_encoder_bf16_tensor_core_path(api, dev, golden):
+    """precision 1: SA1 / SA2 MLPs on tcgen05 (bf16 operands, fp32 accumulate).  Indices are untouched by
+    the precision switch; features within the stated bf16 tolerance rtol 2e-2 / atol 2e-2."""
+    g, enc = load_encoder(api, golden, dev, precision=1)
+    x = torch.from_numpy(g["x"]).to(dev)
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        l1_xyz, l1_pts = enc.sa1(x, None)
+        l2_xyz, l2_pts = enc.sa2(l1_xyz, l1_pts.permute(0, 2, 1))
+    np.testing.assert_allclose(l1_pts.cpu().numpy(), g["l1_points"], rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(l2_pts.cpu().numpy(), g["l2_points"], rtol=2e-2, atol=2e-2)
+    # and the error is bf16-sized, not garbage that happens to sit inside atol
+    err = np.abs(l1_pts.cpu().numpy() - g["l1_points"]).max() / np.abs(g["l1_points"]).max()
+    assert err < 1e-2, err
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        feat = enc(x)
+    np.testing.assert_allclose(feat.cpu().numpy(), g["feature"], rtol=2e-2, atol=2e-2)
+
+
+def test_sa_mlp_tensor_core_ragged_groups(api, dev, oracle):
+    """K not a multiple of 32 and a partial last row tile exercise the per-element pooling path."""
+    torch.manual_seed(0)
+    sa = api.enc.SetAbstraction(20, 0.5, 24, in_channel=5, mlp=[32, 64, 96]).eval().to(dev)
+    sa.mlp_precision = 1
+    for bn in sa.mlp_bns:
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+    pts = torch.randn(3, 20, 24, 8, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        out = sa.apply_mlp(pts.to(dev)).cpu().numpy()
+    sd = {k: v.detach().cpu().numpy() for k, v in sa.state_dict().items()}
+    ref = oracle.apply_mlp(pts.numpy(), oracle.layers_from_state_dict(sd, ""))
+    np.testing.assert_allclose(out, ref, rtol=2e-2, atol=2e-2)
+
+
 def test_graphed_encoder_equals_eager(api, dev, golden):
     from pointcloud_style_transfer_b200.runtime import GraphedEncoder
 
