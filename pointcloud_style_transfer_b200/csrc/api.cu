@@ -31,6 +31,8 @@ static std::map<std::string, int>& tune_map() {
         {"nn_min.variant", 0},        // 0 = auto
         {"nn_min.splits", 0},         // 0 = auto (candidate-range splits per row tile)
         {"fps.cluster", 0},           // 0 = auto (CTAs per cloud)
+        {"fps.threads", 0},           // 0 = auto (32, 128 or 512 threads per CTA)
+        {"fps.prune", 0},             // 0/1 = bounding-box skip test on, 2 = off
         {"sa_mlp.variant", 0},
     };
     return m;

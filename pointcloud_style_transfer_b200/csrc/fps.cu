@@ -5,9 +5,18 @@
 // single launch per batch.  The cloud is split over the CTAs of a cluster (up to 16, the
 // non-portable maximum); every thread keeps P points (x, y, z) and their running minimum
 // distance in registers for the whole kernel, so HBM is touched once (N*12 B in, npoint*8 B out).
-// Per iteration: packed fp32x2 distance update -> per-thread argmax -> REDUX warp argmax ->
-// shared-memory block argmax -> DSMEM all-to-all of (value, index, xyz) by st.async, completion
-// counted on a per-CTA mbarrier (no barrier.cluster / MEMBAR.GPU in the loop).
+//
+// Work layout: the cloud is cut into chunks of 32*P consecutive points; chunk c belongs to warp
+// (c / C) of CTA (c % C), so neighbouring chunks sit on different SMs.  Per iteration and warp:
+//   1. exact skip test: if the chunk's bounding box is at least as far from the new centroid as the
+//      chunk's current maximum running distance (lower bound evaluated with the same fp32 operation
+//      sequence as the distances, which is monotone), no distance in the chunk can change and the
+//      warp re-uses its cached (max, argmax);  clouds whose index order is spatially coherent (LiDAR
+//      scans) skip most chunks after the first few dozen samples;
+//   2. otherwise packed fp32x2 distance update + per-thread argmax + REDUX warp argmax;
+//   3. shared-memory block argmax (one __syncthreads), then a DSMEM all-to-all of
+//      (value, index, xyz) by st.async with completion counted on a per-CTA mbarrier
+//      (no barrier.cluster / MEMBAR.GPU in the loop).
 //
 // Arithmetic (bit-exact with the reference's fp32 CPU path):
 //   d = ((dx*dx) + (dy*dy)) + (dz*dz), no FMA;  dist = min(dist, d), dist0 = 1e10;
@@ -18,55 +27,87 @@
 
 namespace pcst {
 
-constexpr int kFpsThreads = 512;
-constexpr int kFpsWarps = kFpsThreads / 32;
+constexpr int kFpsMaxThreads = 512;
+constexpr int kFpsMaxWarps = kFpsMaxThreads / 32;
 constexpr int kFpsMaxCluster = 16;
 constexpr unsigned kNoIdx = 0xffffffffu;
 
 struct FpsShared {
-    int2 wslot[2][kFpsWarps];          // per-warp (value bits, index), double-buffered by iteration parity
+    int2 wslot[2][kFpsMaxWarps];       // per-warp (value bits, index), double-buffered by iteration parity
     float4 cslot[2][kFpsMaxCluster];   // per-CTA (x, y, z, value) of the CTA's best point
     unsigned cidx[2][kFpsMaxCluster];  // per-CTA index of the CTA's best point
     uint64_t cbar[2];                  // transaction barriers: C x 20 bytes land per use
 };
 
-// P > 0: register-resident, P points per thread (P even).  P == 0: streaming fallback for clouds
-// that do not fit the register file of one cluster: distances live in a global workspace and the
-// points are re-read (from L2) every iteration.
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// one-sided gap between a coordinate interval [lo, hi] and c, rounded exactly like (x - c) is
+__device__ __forceinline__ float box_gap(float lo, float hi, float c) {
+    return fmaxf(fmaxf(__fsub_rn(lo, c), __fsub_rn(c, hi)), 0.0f);
+}
+
+// P > 0: register-resident, P points per thread (P even), blockDim.x in {32, 128, 512}.
+// P == 0: streaming fallback for clouds that do not fit the register file of one cluster: distances
+// live in a global workspace and the points are re-read (from L2) every iteration.
 template <int P>
-__global__ void __launch_bounds__(kFpsThreads, 1)
+__global__ void __launch_bounds__(kFpsMaxThreads, 1)
 fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __restrict__ start,
-           int64_t* __restrict__ out, float* __restrict__ new_xyz, int pts_per_cta, float* __restrict__ dist_ws) {
+           int64_t* __restrict__ out, float* __restrict__ new_xyz, int pts_per_cta, float* __restrict__ dist_ws,
+           int prune) {
     extern __shared__ __align__(16) float smem_pts[];  // P > 0: SoA copy of this CTA's points
     __shared__ FpsShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const unsigned C = cluster_nctarank();
     const unsigned rank = cluster_ctarank();
     const int b = blockIdx.x / C;
     const float* pts = xyz + (size_t)b * N * 3;
-    const int base = rank * pts_per_cta;
-    int count = N - base;
-    if (count > pts_per_cta) count = pts_per_cta;
-    if (count < 0) count = 0;
+
+    // P > 0: chunk of this warp;  P == 0: contiguous range of this CTA
+    constexpr int CH = P > 0 ? 32 * P : 1;
+    const int chunk = warp * (int)C + (int)rank;
+    const int cbase = P > 0 ? chunk * CH : (int)rank * pts_per_cta;
+    const int sbase = warp * CH;  // slot of the chunk inside this CTA's shared-memory copy
+    int count = N - (P > 0 ? 0 : cbase);
+    if (P == 0) {
+        if (count > pts_per_cta) count = pts_per_cta;
+        if (count < 0) count = 0;
+    }
     float* sx = smem_pts;
-    float* sy = smem_pts + pts_per_cta;
-    float* sz = smem_pts + 2 * pts_per_cta;
-    float* gdist = (P == 0) ? dist_ws + (size_t)b * N + base : nullptr;
+    float* sy = smem_pts + nwarps * CH;
+    float* sz = smem_pts + 2 * nwarps * CH;
+    float* gdist = (P == 0) ? dist_ws + (size_t)b * N + cbase : nullptr;
 
     constexpr int PP = P > 0 ? P / 2 : 1;
     float2 px[PP], py[PP], pz[PP], pd[PP];
+    float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f;
+    int cmax = (int)0xbf800000;  // cached warp max (bits of -1.0f: "no valid point")
+    unsigned cidx = kNoIdx;     // cached warp argmax
     if (P > 0) {
+        const float inf = __int_as_float(0x7f800000);
+        float mnx = inf, mny = inf, mnz = inf, mxx = -inf, mxy = -inf, mxz = -inf;
 #pragma unroll
         for (int k = 0; k < PP; ++k) {
             float v[2][4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int l = (2 * k + h) * kFpsThreads + tid;
-                if (l < count) {
-                    const float* q = pts + (size_t)(base + l) * 3;
+                const int l = (2 * k + h) * 32 + lane;
+                if (cbase + l < N) {
+                    const float* q = pts + (size_t)(cbase + l) * 3;
                     v[h][0] = q[0]; v[h][1] = q[1]; v[h][2] = q[2]; v[h][3] = 1e10f;
-                    sx[l] = v[h][0]; sy[l] = v[h][1]; sz[l] = v[h][2];
+                    sx[sbase + l] = v[h][0]; sy[sbase + l] = v[h][1]; sz[sbase + l] = v[h][2];
+                    mnx = fminf(mnx, v[h][0]); mxx = fmaxf(mxx, v[h][0]);
+                    mny = fminf(mny, v[h][1]); mxy = fmaxf(mxy, v[h][1]);
+                    mnz = fminf(mnz, v[h][2]); mxz = fmaxf(mxz, v[h][2]);
                 } else {
                     v[h][0] = v[h][1] = v[h][2] = 0.f; v[h][3] = -1.0f;
                 }
@@ -76,8 +117,14 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
             pz[k] = make_float2(v[0][2], v[1][2]);
             pd[k] = make_float2(v[0][3], v[1][3]);
         }
+        lox = warp_min_f(mnx); loy = warp_min_f(mny); loz = warp_min_f(mnz);
+        hix = warp_max_f(mxx); hiy = warp_max_f(mxy); hiz = warp_max_f(mxz);
+        if (cbase < N) {  // non-empty chunk: every running distance starts at 1e10, lowest index first
+            cmax = __float_as_int(1e10f);
+            cidx = (unsigned)cbase;
+        }
     } else {
-        for (int l = tid; l < count; l += kFpsThreads) gdist[l] = 1e10f;
+        for (int l = tid; l < count; l += nthreads) gdist[l] = 1e10f;
     }
 
     long long far = start[b];
@@ -103,48 +150,69 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         if (it == npoint - 1) break;
         const int par = it & 1;
 
-        // ---- distance update + per-thread argmax (ascending index, strict > keeps the lowest) ----
-        float best = -1.0f;
-        unsigned bi = kNoIdx;
+        int wmax;
+        unsigned widx;
         if (P > 0) {
-            const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+            // ---- exact skip test (warp-uniform) ----
+            const float gx = box_gap(lox, hix, cx), gy = box_gap(loy, hiy, cy), gz = box_gap(loz, hiz, cz);
+            const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+            if (prune && lb >= __int_as_float(cmax)) {
+                wmax = cmax;
+                widx = cidx;
+            } else {
+                // ---- distance update + per-thread argmax (ascending index, strict > keeps the lowest) ----
+                float best = -1.0f;
+                unsigned bi = kNoIdx;
+                const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
 #pragma unroll
-            for (int k = 0; k < PP; ++k) {
-                const float2 dx = __fadd2_rn(px[k], ncx), dy = __fadd2_rn(py[k], ncy), dz = __fadd2_rn(pz[k], ncz);
-                const float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
-                pd[k].x = fminf(pd[k].x, d.x);
-                pd[k].y = fminf(pd[k].y, d.y);
-                if (pd[k].x > best) { best = pd[k].x; bi = base + (2 * k) * kFpsThreads + tid; }
-                if (pd[k].y > best) { best = pd[k].y; bi = base + (2 * k + 1) * kFpsThreads + tid; }
+                for (int k = 0; k < PP; ++k) {
+                    const float2 dx = __fadd2_rn(px[k], ncx), dy = __fadd2_rn(py[k], ncy), dz = __fadd2_rn(pz[k], ncz);
+                    const float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+                    pd[k].x = fminf(pd[k].x, d.x);
+                    pd[k].y = fminf(pd[k].y, d.y);
+                    if (pd[k].x > best) { best = pd[k].x; bi = cbase + (2 * k) * 32 + lane; }
+                    if (pd[k].y > best) { best = pd[k].y; bi = cbase + (2 * k + 1) * 32 + lane; }
+                }
+                // ---- warp argmax: two REDUX instead of a 5-step shuffle tree ----
+                const int vb = __float_as_int(best);
+                wmax = __reduce_max_sync(0xffffffffu, vb);
+                widx = __reduce_min_sync(0xffffffffu, vb == wmax ? bi : kNoIdx);
+                cmax = wmax;
+                cidx = widx;
             }
         } else {
-            for (int l = tid; l < count; l += kFpsThreads) {
-                const float* q = pts + (size_t)(base + l) * 3;
+            float best = -1.0f;
+            unsigned bi = kNoIdx;
+            for (int l = tid; l < count; l += nthreads) {
+                const float* q = pts + (size_t)(cbase + l) * 3;
                 const float dx = __fsub_rn(q[0], cx), dy = __fsub_rn(q[1], cy), dz = __fsub_rn(q[2], cz);
                 const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 const float cur = fminf(gdist[l], d);
                 gdist[l] = cur;
-                if (cur > best) { best = cur; bi = base + l; }
+                if (cur > best) { best = cur; bi = cbase + l; }
             }
+            const int vb = __float_as_int(best);
+            wmax = __reduce_max_sync(0xffffffffu, vb);
+            widx = __reduce_min_sync(0xffffffffu, vb == wmax ? bi : kNoIdx);
         }
 
-        // ---- warp argmax: two REDUX instead of a 5-step shuffle tree ----
-        const int vb = __float_as_int(best);
-        const int wmax = __reduce_max_sync(0xffffffffu, vb);
-        const unsigned widx = __reduce_min_sync(0xffffffffu, vb == wmax ? bi : kNoIdx);
-        if (lane == 0) sh.wslot[par][warp] = make_int2(wmax, (int)widx);
-        __syncthreads();
-
         // ---- block argmax, computed redundantly by every warp ----
-        int2 e = lane < kFpsWarps ? sh.wslot[par][lane] : make_int2((int)0x80000000, (int)kNoIdx);
-        const int bmax = __reduce_max_sync(0xffffffffu, e.x);
-        const unsigned bidx = __reduce_min_sync(0xffffffffu, e.x == bmax ? (unsigned)e.y : kNoIdx);
+        int bmax = wmax;
+        unsigned bidx = widx;
+        if (nwarps > 1) {
+            if (lane == 0) sh.wslot[par][warp] = make_int2(wmax, (int)widx);
+            __syncthreads();
+            int2 e = lane < nwarps ? sh.wslot[par][lane] : make_int2((int)0x80000000, (int)kNoIdx);
+            bmax = __reduce_max_sync(0xffffffffu, e.x);
+            bidx = __reduce_min_sync(0xffffffffu, e.x == bmax ? (unsigned)e.y : kNoIdx);
+        }
+        // shared-memory slot of the block's best point (P > 0)
+        const int bslot = P > 0 ? (int)((bidx / CH) / C) * CH + (int)(bidx % CH) : 0;
 
         if (C == 1) {
             far = bidx;
             if (P > 0) {
-                const int l = (int)bidx - base;
-                cx = sx[l]; cy = sy[l]; cz = sz[l];
+                cx = sx[bslot]; cy = sy[bslot]; cz = sz[bslot];
             } else {
                 const float* q = pts + (size_t)bidx * 3;
                 cx = q[0]; cy = q[1]; cz = q[2];
@@ -158,8 +226,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
                 float x = 0.f, y = 0.f, z = 0.f;
                 if (bidx != kNoIdx) {
                     if (P > 0) {
-                        const int l = (int)bidx - base;
-                        x = sx[l]; y = sy[l]; z = sz[l];
+                        x = sx[bslot]; y = sy[bslot]; z = sz[bslot];
                     } else {
                         const float* q = pts + (size_t)bidx * 3;
                         x = q[0]; y = q[1]; z = q[2];
@@ -199,22 +266,25 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
 }
 
 struct FpsPlan {
-    int C, P, pts_per_cta;
+    int C, P, threads, pts_per_cta;
     size_t smem, ws;
 };
 
 static FpsPlan fps_plan(int B, int N) {
     FpsPlan p;
     int C = tuning("fps.cluster", 0);
-    if (C == 0) C = N <= 4096 ? 1 : (N <= 16384 ? 4 : (N <= 65536 ? 8 : 16));
+    if (C == 0) C = N <= 8192 ? 1 : (N <= 16384 ? 4 : (N <= 65536 ? 8 : 16));
     if (C > kFpsMaxCluster) C = kFpsMaxCluster;
     p.C = C;
-    int per = (N + C - 1) / C;
-    per = (int)align_up((size_t)per, 32);
-    p.pts_per_cta = per;
-    p.P = per <= 2 * kFpsThreads ? 2 : per <= 4 * kFpsThreads ? 4 : per <= 8 * kFpsThreads ? 8
-          : per <= 16 * kFpsThreads ? 16 : 0;
-    p.smem = p.P > 0 ? (size_t)3 * per * sizeof(float) : 0;
+    int threads = tuning("fps.threads", 0);
+    if (threads == 0) threads = (C == 1 && N <= 512) ? 32 : ((C == 1 && N <= 2048) ? 128 : kFpsMaxThreads);
+    if (threads != 32 && threads != 128) threads = kFpsMaxThreads;
+    p.threads = threads;
+    const long lanes = (long)threads * C;                 // threads that share one cloud
+    const long per_thread = (N + lanes - 1) / lanes;
+    p.P = per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 8 ? 8 : per_thread <= 16 ? 16 : 0;
+    p.pts_per_cta = p.P > 0 ? threads * p.P : (int)align_up((size_t)((N + C - 1) / C), 32);
+    p.smem = p.P > 0 ? (size_t)3 * p.pts_per_cta * sizeof(float) : 0;
     p.ws = p.P > 0 ? 0 : align_up((size_t)B * N * sizeof(float), 256);
     return p;
 }
@@ -228,7 +298,7 @@ static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoi
     if (p.C > 8) PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * p.C);
-    cfg.blockDim = dim3(kFpsThreads);
+    cfg.blockDim = dim3(p.threads);
     cfg.dynamicSmemBytes = p.smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -239,7 +309,8 @@ static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoi
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int pts_per_cta = p.pts_per_cta;
-    PCST_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, out, new_xyz, pts_per_cta, dist_ws));
+    int prune = tuning("fps.prune", 1) != 2;  // 2 = off (for A/B measurements)
+    PCST_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, out, new_xyz, pts_per_cta, dist_ws, prune));
     return PCST_OK;
 }
 

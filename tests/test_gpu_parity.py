@@ -80,6 +80,25 @@ def test_fps_every_cluster_size(api, dev, oracle, cluster):
     assert np.array_equal(idx, oracle.farthest_point_sample(x, 200, start))
 
 
+@pytest.mark.parametrize("threads", [32, 128, 512])
+def test_fps_every_block_size_and_skip_test_off(api, dev, oracle, threads):
+    from pointcloud_style_transfer_b200 import _lib
+
+    x = S.lidar_scan(3, 512 if threads == 32 else 2000).numpy()
+    N = x.shape[1]
+    start = np.array([5], np.int64)
+    ref = oracle.farthest_point_sample(x, 64, start)
+    for prune in (1, 2):
+        _lib.set_tuning("fps.threads", threads)
+        _lib.set_tuning("fps.prune", prune)
+        try:
+            idx, _ = run_fps(api, dev, x, 64, start)
+        finally:
+            _lib.set_tuning("fps.threads", 0)
+            _lib.set_tuning("fps.prune", 0)
+        assert np.array_equal(idx, ref), (threads, prune, N)
+
+
 def test_fps_streaming_fallback_large_cloud(api, dev, oracle):
     N = 150000  # > 16 CTAs x 8192 register-resident points
     x = S.uniform_cloud(4, 1, N).numpy()

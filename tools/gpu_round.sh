@@ -12,6 +12,8 @@ timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpu
 echo "bench exit $?"
 tail -3 gpurun_out/bench.err
 cat gpurun_out/bench.json
+timeout 600 python bench.py --steps 20 --warmup 5 --mlp-precision 1 --no-cpu-baseline > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
+echo "bench bf16 exit $?"; cat gpurun_out/bench_bf16.json
 timeout 300 python tools/prof_kernels.py > gpurun_out/kernels.log 2>&1
 echo "prof exit $?"; cat gpurun_out/kernels.log
 if [ "${NCU:-0}" = "1" ]; then

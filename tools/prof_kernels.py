@@ -32,7 +32,28 @@ def timeit(name, fn, reps=5):
 
 
 if "fps" in which:
-    timeit("fps 120k->512", lambda: ops.fps(x, 512, start))
+    from pointcloud_style_transfer_b200 import _lib
+    timeit("fps 120k->512 (lidar order)", lambda: ops.fps(x, 512, start))
+    _lib.set_tuning("fps.prune", 2)
+    timeit("fps 120k->512 (lidar order, no skip test)", lambda: ops.fps(x, 512, start))
+    _lib.set_tuning("fps.prune", 0)
+    xu = S.uniform_cloud(0, 1, 120000).to(dev)
+    timeit("fps 120k->512 (uniform random order)", lambda: ops.fps(xu, 512, start))
+    for c in (4, 8, 16):
+        _lib.set_tuning("fps.cluster", c)
+        x16 = S.uniform_cloud(0, 4, 16384).to(dev)
+        timeit(f"fps 4x16384->512 cluster={c}", lambda: ops.fps(x16, 512, torch.zeros(4, dtype=torch.long, device=dev)))
+    _lib.set_tuning("fps.cluster", 0)
+    x4k = S.uniform_cloud(0, 2, 4096).to(dev)
+    for c in (1, 2, 4):
+        _lib.set_tuning("fps.cluster", c)
+        timeit(f"fps 2x4096->512 cluster={c}", lambda: ops.fps(x4k, 512, torch.zeros(2, dtype=torch.long, device=dev)))
+    _lib.set_tuning("fps.cluster", 0)
+    for t in (32, 128, 512):
+        _lib.set_tuning("fps.threads", t)
+        x512 = S.uniform_cloud(0, 1, 512).to(dev)
+        timeit(f"fps 512->128 threads={t}", lambda: ops.fps(x512, 128, start * 0))
+    _lib.set_tuning("fps.threads", 0)
     x16 = S.uniform_cloud(0, 4, 16384).to(dev)
     st4 = torch.zeros(4, dtype=torch.long, device=dev)
     timeit("fps 4x16384->512", lambda: ops.fps(x16, 512, st4))
@@ -49,11 +70,12 @@ if "enc" in which or "mlp" in which:
     torch.manual_seed(42)
     for prec in (0, 1):
         enc = PointNet2Encoder(feature_dim=256, mlp_precision=prec).eval().to(dev)
-        try:
-            with torch.no_grad():
-                timeit(f"encoder eager precision={prec}", lambda: enc(x))
-        except Exception as e:  # the tensor-core path may not be built yet
-            print(f"encoder precision={prec}: {type(e).__name__}: {str(e)[:120]}")
+        with torch.no_grad():
+            timeit(f"encoder eager precision={prec}", lambda: enc(x))
+            ops.start_event_log()
+            enc(x)
+            log = ops.stop_event_log()
+        print("   per-op us:", {k: [round(v * 1e3, 1) for v in vs] for k, vs in log.items()}, flush=True)
 if "knn" in which:
     q, r = S.uniform_cloud(1, 1, 90000).to(dev), S.uniform_cloud(2, 1, 30000).to(dev)
     timeit("knn 90k x 30k k=3", lambda: ops.knn(q, r, 3), reps=2)
