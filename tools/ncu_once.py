@@ -26,6 +26,7 @@ for rep in range(2):  # pass 0 warms up (module load, function attributes), pass
             enc(x)                      # fps x2, ball query x2, sa_mlp x3 (fp32 then tcgen05)
         ops.nn_min(x, y, 0, False)      # Chamfer direction, loss form
         ops.nn_min(x, y, 0, True)       # with argmin (training)
+        ops.nn_min_pair(x, y, 0)        # both Chamfer directions in one sweep
         ops.knn(q, r, 3)                # upsample_knn search
     torch.cuda.synchronize()
 print("ncu_once ok")

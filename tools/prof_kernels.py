@@ -36,6 +36,8 @@ if "fps" in which:
     timeit("fps 120k->512 (lidar order)", lambda: ops.fps(x, 512, start))
     _lib.set_tuning("fps.prune", 2)
     timeit("fps 120k->512 (lidar order, no skip test)", lambda: ops.fps(x, 512, start))
+    _lib.set_tuning("fps.prune", 3)
+    timeit("fps 120k->512 (exchange chain only: every chunk skipped, results invalid)", lambda: ops.fps(x, 512, start))
     _lib.set_tuning("fps.prune", 0)
     xu = S.uniform_cloud(0, 1, 120000).to(dev)
     timeit("fps 120k->512 (uniform random order)", lambda: ops.fps(xu, 512, start))
@@ -66,6 +68,8 @@ if "nn" in which:
     timeit("nn_min 120k x 120k form0", lambda: ops.nn_min(x, y, 0, False), reps=3)
     timeit("nn_min 120k x 120k form0 +arg", lambda: ops.nn_min(x, y, 0, True), reps=3)
     timeit("nn_min 120k x 120k form1", lambda: ops.nn_min(x, y, 1, False), reps=3)
+    timeit("nn_min_pair 120k x 120k form0 (both directions, one sweep)", lambda: ops.nn_min_pair(x, y, 0), reps=3)
+    timeit("nn_min_pair 120k x 120k form1", lambda: ops.nn_min_pair(x, y, 1), reps=3)
 if "enc" in which or "mlp" in which:
     torch.manual_seed(42)
     for prec in (0, 1):
