@@ -129,6 +129,16 @@ size_t pcst_nn_min_workspace_bytes(int B, int N, int M);
 int pcst_nn_min_f32(const float* a, const float* b, int B, int N, int M, int form, float* rowmin,
                     int64_t* rowarg, void* ws, size_t ws_bytes, pcst_stream_t stream);
 
+/* Both directions of the same pair matrix in ONE sweep (each pair evaluated once): the matrix of the second
+ * direction is bit-for-bit the transpose of the first, for the loss (models/losses.py:36-41 vs 53-58) and for
+ * torch.cdist (evaluation/metrics.py:32: dist.min(dim=2) / dist.min(dim=1)).
+ *  form 0: rowmin [B,N] = pcst_nn_min_f32(a, b, form 0), colmin [B,M] = pcst_nn_min_f32(b, a, form 0);
+ *  form 1: a = cdist's x1: rowmin = form 1 of (a, b), colmin = form 2 of (b, a).
+ * Values are identical to the two one-directional calls; no argmin (use pcst_nn_min_f32 for backward). */
+size_t pcst_nn_min_pair_workspace_bytes(int B, int N, int M);
+int pcst_nn_min_pair_f32(const float* a, const float* b, int B, int N, int M, int form, float* rowmin,
+                         float* colmin, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
 /* Backward of chamfer_distance_chunked_optimized (autograd of models/losses.py:24-61).
  * pred [B,N,3], target [B,M,3]; arg_pt [B,N] / arg_tp [B,M] = the argmins returned by pcst_nn_min_f32
  * (form 0) for pred->target / target->pred; grad_out [B] = dL/d(chamfer[b]).

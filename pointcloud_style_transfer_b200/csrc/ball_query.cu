@@ -2,26 +2,67 @@
 //
 // The reference materialises an int64 [B,S,N] index tensor and a fp32 [B,S,N] distance matrix and
 // sorts the former along N.  Here the same full S x N sweep is done in two small kernels:
-//   1. bq_mask_kernel: CTA = (candidate tile of 1024 points) x (128 queries).  The tile is staged in
-//      shared memory as packed float4 by one 1-D TMA bulk copy and broadcast to all threads; each
-//      thread owns one query and evaluates the predicate NOT(D > r^2) in the reference's exact fp32
-//      rounding (D = ((-2*dot) + |q|^2) + |p|^2, dot as an FMA chain), packing 32 candidates per
-//      32-bit word: a [B,S,N/32] bit matrix (1 bit per pair instead of the reference's 12 bytes).
-//   2. bq_emit_kernel: one warp per query walks its bit row in index order (popc + warp scan),
-//      emits the first nsample set bits, stops early, pads short rows with the first hit / N.
+//   1. bq_mask_kernel: CTA = (candidate tile of 1024 points) x (128 queries).  The tile's raw xyz rows
+//      (12 KiB) are staged in shared memory by one 1-D TMA bulk copy, repacked there to float4
+//      (x, y, z, |p|^2) and broadcast to all threads; each thread owns one query and evaluates the
+//      predicate NOT(D > r^2) in the reference's exact fp32 rounding (D = ((-2*dot) + |q|^2) + |p|^2,
+//      dot as an FMA chain), packing 32 candidates per 32-bit word: a [B,S,N/32] bit matrix (1 bit
+//      per pair instead of the reference's 12 bytes).
+//   2. bq_emit_kernel: one CTA per query reads its bit row with wide independent loads, scans the hit
+//      counts (popc + warp scan + 8-entry block scan) and emits the first nsample set bits in index
+//      order, pads short rows with the first hit / N.
 // Rows are identical to sort-and-slice because set bits are visited in ascending index order.
-// Bound: FP32 CUDA cores (0.49 GFLOP per 512 x 120k sweep, ~9 issue slots per pair); HBM traffic:
-// N*16 B packed points + S*N/8 B of bits, all L2-resident.
+// Clouds of at most 2048 points (the second set-abstraction stage) take a single fused launch instead
+// (bq_small_kernel).  Bound: FP32 CUDA cores (0.49 GFLOP per 512 x 120k sweep, ~9 issue slots per
+// pair); HBM traffic: N*12 B of points + S*N/8 B of bits, all L2-resident.
 #include "common.cuh"
 
 namespace pcst {
 
 constexpr int kBQThreads = 128;  // queries per CTA in the mask kernel
 
+// Stage the raw [n,3] fp32 rows of one candidate tile in shared memory and repack them to float4
+// (x, y, z, |p|^2) with the reference's norm rounding; slots n..kTilePoints-1 become +inf sentinels.
+// Full, 16-byte aligned tiles arrive by one 1-D TMA bulk copy; a ragged or misaligned tile is read
+// with coalesced loads.  Called by all threads of the CTA; ends with a __syncthreads.
+__device__ __forceinline__ void bq_stage_tile(const float* __restrict__ src, int n, float* raw, float4* tile,
+                                              uint64_t* bar, uint32_t parity) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const bool bulk = (n == kTilePoints) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (bulk) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, kTilePoints * 12);
+            tma_load_1d(raw, src, kTilePoints * 12, bar);
+        }
+        mbar_wait(bar, parity);
+    } else {
+        for (int e = tid; e < n * 3; e += nthreads) raw[e] = src[e];
+        __syncthreads();
+    }
+    for (int i = tid; i < kTilePoints; i += nthreads) {
+        float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+        if (i < n) {
+            v.x = raw[3 * i]; v.y = raw[3 * i + 1]; v.z = raw[3 * i + 2];
+            v.w = norm3_sq(v.x, v.y, v.z);
+        }
+        tile[i] = v;
+    }
+    __syncthreads();
+}
+
+// NOT(D > r^2) with D = ((-2 * dot) + |q|^2) + |p|^2 in the reference's rounding (pointnet2_encoder.py:12-14,54)
+__device__ __forceinline__ bool bq_inside(float qx, float qy, float qz, float qn, const float4& p, float radius_sq) {
+    float d = -2.0f * dot3_chain(qx, qy, qz, p.x, p.y, p.z);  // exact scaling
+    d = __fadd_rn(d, qn);
+    d = __fadd_rn(d, p.w);  // sentinel rows have |p|^2 = +inf -> never inside
+    return !(d > radius_sq);
+}
+
 __global__ void __launch_bounds__(kBQThreads)
-bq_mask_kernel(const float4* __restrict__ P, const float* __restrict__ new_xyz, int Npad, int S, float radius_sq,
-               unsigned int* __restrict__ mask) {
+bq_mask_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int Npad, int S,
+               float radius_sq, unsigned int* __restrict__ mask) {
     __shared__ __align__(128) float4 tile[kTilePoints];
+    __shared__ __align__(128) float raw[kTilePoints * 3];
     __shared__ unsigned int words[kBQThreads][33];
     __shared__ __align__(8) uint64_t full_bar;
 
@@ -36,17 +77,15 @@ bq_mask_kernel(const float4* __restrict__ P, const float* __restrict__ new_xyz, 
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&full_bar, kTileBytes);
-        tma_load_1d(tile, P + (size_t)b * Npad + (size_t)t * kTilePoints, kTileBytes, &full_bar);
-    }
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (s < S) {
         const float* q = new_xyz + ((size_t)b * S + s) * 3;
         qx = q[0]; qy = q[1]; qz = q[2];
     }
     const float qn = norm3_sq(qx, qy, qz);
-    mbar_wait(&full_bar, 0);
+    int n = N - t * kTilePoints;
+    if (n > kTilePoints) n = kTilePoints;
+    bq_stage_tile(xyz + ((size_t)b * N + (size_t)t * kTilePoints) * 3, n, raw, tile, &full_bar, 0);
 
 #pragma unroll 1
     for (int c = 0; c < kTilePoints / 32; ++c) {
@@ -54,10 +93,7 @@ bq_mask_kernel(const float4* __restrict__ P, const float* __restrict__ new_xyz, 
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const float4 p = tile[c * 32 + i];  // same address for every thread: shared-memory broadcast
-            float d = -2.0f * dot3_chain(qx, qy, qz, p.x, p.y, p.z);  // exact scaling
-            d = __fadd_rn(d, qn);
-            d = __fadd_rn(d, p.w);  // sentinel rows have |p|^2 = +inf -> never inside
-            w |= (d > radius_sq ? 0u : 1u) << i;
+            w |= (bq_inside(qx, qy, qz, qn, p, radius_sq) ? 1u : 0u) << i;
         }
         words[tid][c] = w;
     }
@@ -69,43 +105,118 @@ bq_mask_kernel(const float4* __restrict__ P, const float* __restrict__ new_xyz, 
     }
 }
 
-__global__ void __launch_bounds__(128)
-bq_emit_kernel(const unsigned int* __restrict__ mask, int N, int Npad, int S, int nsample, int64_t* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Small clouds (N <= kBQSmallMax: the second set-abstraction stage, 512 candidates): one launch, no
+// workspace.  The CTA stages the whole cloud in shared memory; each warp owns one query and walks the
+// candidates in index order, 32 per step (predicate -> ballot -> ordered emit), stopping after nsample hits.
+constexpr int kBQSmallMax = 2 * kTilePoints;
+
+__global__ void __launch_bounds__(kBQThreads)
+bq_small_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, float radius_sq,
+                int nsample, int64_t* __restrict__ out) {
+    __shared__ __align__(128) float4 tile[kBQSmallMax];
+    __shared__ __align__(128) float raw[kTilePoints * 3];
+    __shared__ __align__(8) uint64_t full_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int ntiles = (N + kTilePoints - 1) / kTilePoints;
+    for (int t = 0; t < ntiles; ++t) {
+        int n = N - t * kTilePoints;
+        if (n > kTilePoints) n = kTilePoints;
+        bq_stage_tile(xyz + ((size_t)b * N + (size_t)t * kTilePoints) * 3, n, raw, tile + t * kTilePoints, &full_bar,
+                      (uint32_t)(t & 1));
+    }
+    const int s = blockIdx.x * (kBQThreads / 32) + warp;
     if (s >= S) return;  // whole warp
-    const int words_per_row = Npad / 32;
+    const float* q = new_xyz + ((size_t)b * S + s) * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    const float qn = norm3_sq(qx, qy, qz);
+    int64_t* row = out + ((size_t)b * S + s) * nsample;
+    int cnt = 0, first = N;
+    for (int base = 0; base < N && cnt < nsample; base += 32) {
+        const bool in = bq_inside(qx, qy, qz, qn, tile[base + lane], radius_sq);  // slots >= N are sentinels
+        const unsigned int hits = __ballot_sync(0xffffffffu, in);
+        if (hits == 0u) continue;
+        if (cnt == 0) first = base + __ffs(hits) - 1;
+        const int pos = cnt + __popc(hits & ((1u << lane) - 1u));
+        if (in && pos < nsample) row[pos] = base + lane;
+        cnt += __popc(hits);
+    }
+    for (int k = cnt + lane; k < nsample; k += 32) row[k] = first;  // pad: first hit, or N for an empty ball (:56-58)
+}
+
+// One CTA of 8 warps per query.  The bit row is cut into rounds of 8 x 512 words; in a round every lane
+// loads its 16 consecutive words with four independent 128-bit loads (one memory round trip per round, the
+// whole 120k-candidate row is a single round), counts its hits, and a warp scan + an 8-entry shared-memory
+// scan give each lane the output position of its first hit, so hits are emitted in ascending index order.
+constexpr int kEmitWarps = 8;
+constexpr int kEmitWordsPerLane = 16;
+constexpr int kEmitRound = kEmitWarps * 32 * kEmitWordsPerLane;  // words per round
+
+__global__ void __launch_bounds__(kEmitWarps * 32)
+bq_emit_kernel(const unsigned int* __restrict__ mask, int N, int Npad, int S, int nsample, int64_t* __restrict__ out) {
+    __shared__ int wcount[kEmitWarps];
+    __shared__ int wfirst[kEmitWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x, b = blockIdx.y;
+    const int words_per_row = Npad / 32;  // a multiple of 32: rows are 128-byte aligned
     const unsigned int* row_bits = mask + ((size_t)b * S + s) * words_per_row;
     int64_t* row = out + ((size_t)b * S + s) * nsample;
-    int cnt = 0;
-    int first = N;
-    for (int base = 0; base < words_per_row && cnt < nsample; base += 32) {
-        unsigned int w = base + lane < words_per_row ? row_bits[base + lane] : 0u;
-        const unsigned int any = __ballot_sync(0xffffffffu, w != 0u);
-        if (any == 0u) continue;
-        if (cnt == 0) {
-            const int fl = __ffs(any) - 1;
-            const unsigned int fw = __shfl_sync(0xffffffffu, w, fl);
-            first = (base + fl) * 32 + (__ffs(fw) - 1);
+    constexpr int kNone = 0x7fffffff;
+    int cnt = 0;     // hits emitted or skipped so far (CTA-uniform)
+    int first = N;   // index of the row's first hit; N = none yet (pointnet2_encoder.py:56-58)
+    for (int base = 0; base < words_per_row && cnt < nsample; base += kEmitRound) {
+        const int w0 = base + warp * (32 * kEmitWordsPerLane) + lane * kEmitWordsPerLane;
+        unsigned int w[kEmitWordsPerLane];
+#pragma unroll
+        for (int q = 0; q < kEmitWordsPerLane / 4; ++q) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (w0 + 4 * q < words_per_row) v = __ldg(reinterpret_cast<const uint4*>(row_bits + w0 + 4 * q));
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
         }
-        const int c = __popc(w);
+        int c = 0, myfirst = kNone;
+#pragma unroll
+        for (int k = kEmitWordsPerLane - 1; k >= 0; --k) {
+            c += __popc(w[k]);
+            if (w[k] != 0u) myfirst = (w0 + k) * 32 + (__ffs(w[k]) - 1);
+        }
         int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        int pos = cnt + incl - c;
-        while (w != 0u && pos < nsample) {
-            const int bit = __ffs(w) - 1;
-            row[pos++] = (int64_t)(base + lane) * 32 + bit;
-            w &= w - 1u;
+        const unsigned int any = __ballot_sync(0xffffffffu, c > 0);
+        const int wf = __shfl_sync(0xffffffffu, myfirst, any ? __ffs(any) - 1 : 0);
+        if (lane == 31) wcount[warp] = incl;
+        if (lane == 0) wfirst[warp] = any ? wf : kNone;
+        __syncthreads();
+        int before = cnt, total = cnt;
+#pragma unroll
+        for (int x = 0; x < kEmitWarps; ++x) {
+            const int wc = wcount[x];
+            if (x < warp) before += wc;
+            total += wc;
+            if (first == N && wfirst[x] != kNone) first = wfirst[x];
         }
-        cnt += __shfl_sync(0xffffffffu, incl, 31);
+        int pos = before + incl - c;
+#pragma unroll
+        for (int k = 0; k < kEmitWordsPerLane; ++k) {
+            unsigned int bitsk = w[k];
+            while (bitsk != 0u && pos < nsample) {
+                row[pos++] = (int64_t)(w0 + k) * 32 + (__ffs(bitsk) - 1);
+                bitsk &= bitsk - 1u;
+            }
+        }
+        cnt = total;
+        __syncthreads();  // wcount / wfirst are rewritten in the next round
     }
     // pad short rows with the first hit; empty rows with N (models/pointnet2_encoder.py:56-58)
-    for (int k = cnt + lane; k < nsample; k += 32) row[k] = first;
+    for (int k = cnt + tid; k < nsample; k += kEmitWarps * 32) row[k] = first;
 }
 
 // square_distance, materialised [B,N,M]: 4 B written per pair -> HBM-write bound.
@@ -133,8 +244,9 @@ using namespace pcst;
 
 extern "C" size_t pcst_ball_query_workspace_bytes(int B, int N, int S) {
     if (B <= 0 || N <= 0 || S <= 0) return 0;
+    if (N <= kBQSmallMax) return 0;  // single fused launch, no scratch
     const size_t npad = padded_points(N);
-    return align_up((size_t)B * npad * sizeof(float4), 256) + align_up((size_t)B * S * (npad / 32) * sizeof(unsigned int), 256);
+    return align_up((size_t)B * S * (npad / 32) * sizeof(unsigned int), 256);
 }
 
 extern "C" int pcst_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int S, float radius_sq,
@@ -144,21 +256,25 @@ extern "C" int pcst_ball_query_f32(const float* xyz, const float* new_xyz, int B
     PCST_CHECK_ARG(B > 0 && N > 0 && S > 0, "B, N, S must be positive");
     PCST_CHECK_ARG(B <= 65535, "B must be <= 65535");
     PCST_CHECK_ARG(nsample >= 1 && nsample <= N, "nsample must be in [1, N] (the reference raises for nsample > N)");
+    if (N <= kBQSmallMax) {
+        PCST_CHECK_ARG((S + 3) / 4 <= 0x7fffffff, "S too large");
+        bq_small_kernel<<<dim3((S + 3) / 4, B), kBQThreads, 0, stream>>>(xyz, new_xyz, N, S, radius_sq, nsample, out);
+        return check_cuda(cudaGetLastError(), "bq_small_kernel");
+    }
     const size_t need = pcst_ball_query_workspace_bytes(B, N, S);
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 255)) {
         set_error("pcst_ball_query_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need);
         return PCST_ERR_WORKSPACE;
     }
     const int Npad = padded_points(N);
-    float4* P = (float4*)ws;
-    unsigned int* mask = (unsigned int*)((char*)ws + align_up((size_t)B * Npad * sizeof(float4), 256));
-    int st = launch_pack(xyz, B, N, Npad, P, stream);
-    if (st != PCST_OK) return st;
+    unsigned int* mask = (unsigned int*)ws;
     const int qblocks = (S + kBQThreads - 1) / kBQThreads;
     PCST_CHECK_ARG(qblocks <= 65535, "S too large");
-    bq_mask_kernel<<<dim3(Npad / kTilePoints, qblocks, B), kBQThreads, 0, stream>>>(P, new_xyz, Npad, S, radius_sq, mask);
+    bq_mask_kernel<<<dim3(Npad / kTilePoints, qblocks, B), kBQThreads, 0, stream>>>(xyz, new_xyz, N, Npad, S, radius_sq,
+                                                                                    mask);
     PCST_CUDA(cudaGetLastError());
-    bq_emit_kernel<<<dim3((S + 3) / 4, B), 128, 0, stream>>>(mask, N, Npad, S, nsample, out);
+    PCST_CHECK_ARG(B <= 65535, "B must be <= 65535");
+    bq_emit_kernel<<<dim3(S, B), kEmitWarps * 32, 0, stream>>>(mask, N, Npad, S, nsample, out);
     return check_cuda(cudaGetLastError(), "bq_emit_kernel");
 }
 

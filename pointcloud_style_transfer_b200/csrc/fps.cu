@@ -61,7 +61,7 @@ template <int P>
 __global__ void __launch_bounds__(kFpsMaxThreads, 1)
 fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __restrict__ start,
            int64_t* __restrict__ out, float* __restrict__ new_xyz, int pts_per_cta, float* __restrict__ dist_ws,
-           int prune) {
+           int prune, int log2c) {
     extern __shared__ __align__(16) float smem_pts[];  // P > 0: SoA copy of this CTA's points
     __shared__ FpsShared sh;
 
@@ -69,7 +69,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const unsigned C = cluster_nctarank();
     const unsigned rank = cluster_ctarank();
-    const int b = blockIdx.x / C;
+    const int b = blockIdx.x >> log2c;  // the cluster size is a power of two
     const float* pts = xyz + (size_t)b * N * 3;
 
     // P > 0: chunk of this warp;  P == 0: contiguous range of this CTA
@@ -156,7 +156,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
             // ---- exact skip test (warp-uniform) ----
             const float gx = box_gap(lox, hix, cx), gy = box_gap(loy, hiy, cy), gz = box_gap(loz, hiz, cz);
             const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-            if (prune && lb >= __int_as_float(cmax)) {
+            if ((prune && lb >= __int_as_float(cmax)) || (prune == 3 && it > 0)) {
                 wmax = cmax;
                 widx = cidx;
             } else {
@@ -207,7 +207,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
             bidx = __reduce_min_sync(0xffffffffu, e.x == bmax ? (unsigned)e.y : kNoIdx);
         }
         // shared-memory slot of the block's best point (P > 0)
-        const int bslot = P > 0 ? (int)((bidx / CH) / C) * CH + (int)(bidx % CH) : 0;
+        const int bslot = P > 0 ? (int)((bidx / CH) >> log2c) * CH + (int)(bidx % CH) : 0;
 
         if (C == 1) {
             far = bidx;
@@ -273,8 +273,10 @@ struct FpsPlan {
 static FpsPlan fps_plan(int B, int N) {
     FpsPlan p;
     int C = tuning("fps.cluster", 0);
-    if (C == 0) C = N <= 8192 ? 1 : (N <= 16384 ? 4 : (N <= 65536 ? 8 : 16));
+    if (C == 0) C = N <= 8192 ? 1 : (N <= 32768 ? 8 : 16);
     if (C > kFpsMaxCluster) C = kFpsMaxCluster;
+    while (C & (C - 1)) C &= C - 1;  // power of two (the kernel shifts by log2 C)
+    if (C < 1) C = 1;
     p.C = C;
     int threads = tuning("fps.threads", 0);
     if (threads == 0) threads = (C == 1 && N <= 512) ? 32 : ((C == 1 && N <= 2048) ? 128 : kFpsMaxThreads);
@@ -309,8 +311,13 @@ static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoi
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int pts_per_cta = p.pts_per_cta;
-    int prune = tuning("fps.prune", 1) != 2;  // 2 = off (for A/B measurements)
-    PCST_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, out, new_xyz, pts_per_cta, dist_ws, prune));
+    // 2 = off (for A/B measurements); 3 = skip every chunk after the first iteration (WRONG results:
+    // measures the latency floor of the exchange chain alone)
+    int prune = tuning("fps.prune", 1);
+    prune = prune == 2 ? 0 : prune;
+    int log2c = 0;
+    while ((1 << log2c) < p.C) ++log2c;
+    PCST_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, out, new_xyz, pts_per_cta, dist_ws, prune, log2c));
     return PCST_OK;
 }
 

@@ -49,6 +49,13 @@ __device__ __forceinline__ float pair_dist(float ax, float ay, float az, float a
     }
 }
 
+// 3-input minimum (sm_100: one FMNMX3 on the half-rate ALU pipe instead of two FMNMX)
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 template <int FORM, int R, bool ARG, bool VEC2>
 __global__ void __launch_bounds__(kNNThreads, 2)
 nn_min_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N, int Npad, int Mpad,
@@ -104,33 +111,26 @@ nn_min_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N
         const float4* tile = tiles + (size_t)s * kTilePoints;
         const int jbase = (tile0 + t) * kTilePoints;
         if (!ARG && VEC2 && (R % 2 == 0)) {
-            // packed fp32x2 path: two rows per FFMA2 / FADD2 / FMUL2 issue slot
-#pragma unroll 4
-            for (int j = 0; j < kTilePoints; ++j) {
-                const float4 c = tile[j];
+            // packed fp32x2 path: two rows per FFMA2 / FADD2 / FMUL2 issue slot, two candidates per
+            // FMNMX3 (the minimum runs on the half-rate ALU pipe)
+            auto pair2 = [&](const float4& c, int r) -> float2 {
                 const float2 cx = make_float2(c.x, c.x), cy = make_float2(c.y, c.y), cz = make_float2(c.z, c.z),
                              cw = make_float2(c.w, c.w);
+                const float2 vx = make_float2(ax[r], ax[r + 1]), vy = make_float2(ay[r], ay[r + 1]),
+                             vz = make_float2(az[r], az[r + 1]), vn = make_float2(an[r], an[r + 1]);
+                const float2 dot = __ffma2_rn(vz, cz, __ffma2_rn(vy, cy, __fmul2_rn(vx, cx)));
+                if (FORM == 0) return __ffma2_rn(make_float2(-2.0f, -2.0f), dot, __fadd2_rn(vn, cw));
+                if (FORM == 1) return __fadd2_rn(__fadd2_rn(dot, vn), cw);
+                return __fadd2_rn(__fadd2_rn(dot, cw), vn);
+            };
+#pragma unroll 4
+            for (int j = 0; j < kTilePoints; j += 2) {
+                const float4 c0 = tile[j], c1 = tile[j + 1];
 #pragma unroll
                 for (int r = 0; r < R; r += 2) {
-                    const float2 vx = make_float2(ax[r], ax[r + 1]), vy = make_float2(ay[r], ay[r + 1]),
-                                 vz = make_float2(az[r], az[r + 1]), vn = make_float2(an[r], an[r + 1]);
-                    float2 d;
-                    if (FORM == 0) {
-                        float2 tt = __fadd2_rn(vn, cw);
-                        float2 dot = __ffma2_rn(vz, cz, __ffma2_rn(vy, cy, __fmul2_rn(vx, cx)));
-                        d = __ffma2_rn(make_float2(-2.0f, -2.0f), dot, tt);
-                    } else {
-                        float2 rr = __ffma2_rn(vz, cz, __ffma2_rn(vy, cy, __fmul2_rn(vx, cx)));
-                        if (FORM == 1) {
-                            rr = __fadd2_rn(rr, vn);
-                            d = __fadd2_rn(rr, cw);
-                        } else {
-                            rr = __fadd2_rn(rr, cw);
-                            d = __fadd2_rn(rr, vn);
-                        }
-                    }
-                    best[r] = fminf(best[r], d.x);
-                    best[r + 1] = fminf(best[r + 1], d.y);
+                    const float2 d0 = pair2(c0, r), d1 = pair2(c1, r);
+                    best[r] = fmin3(best[r], d0.x, d1.x);
+                    best[r + 1] = fmin3(best[r + 1], d0.y, d1.y);
                 }
             }
         } else {
@@ -175,6 +175,148 @@ nn_min_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N
     }
 }
 
+
+
+// ---- both directions in one sweep ------------------------------------------------------------
+// The second direction's pair matrix of the Chamfer loss is bit-for-bit the transpose of the first
+// (the K=3 FMA chain and the norm sum are symmetric in their arguments), and
+// the same holds for the rows / columns of torch.cdist.  nn_min_pair_kernel therefore evaluates every
+// pair ONCE and reduces it into a row minimum (registers, as above) and a column minimum:
+//   per candidate: minimum over the thread's R rows (FMNMX3 tree) -> clamp -> warp minimum with one
+//   REDUX on the IEEE bits (non-negative floats order like unsigned integers) -> lane (j mod 32) keeps
+//   it -> one STS per 32 candidates into the warp's private column strip -> after the tile, the eight
+//   strips are merged and sent to HBM with atomicMin (4 B per candidate per CTA and tile).
+// Work per pair: 5 FP32-pipe lane operations + ~1.1 ALU-pipe operations, against 2 x (5 + 1) for two
+// one-directional sweeps.
+constexpr int kPairR = 8;       // rows per thread
+constexpr int kPairStages = 2;  // a 1024-candidate tile is ~50 us of work per CTA: two stages hide the 16 KiB copy
+
+template <int FORM>
+__global__ void __launch_bounds__(kNNThreads, 2)
+nn_min_pair_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N, int M, int Npad, int Mpad,
+                   int tiles_per_split, unsigned int* __restrict__ rowmin_bits, unsigned int* __restrict__ colmin_bits) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);                                         // [stages][1024]
+    unsigned int* colw = reinterpret_cast<unsigned int*>(smem_raw + kPairStages * kTileBytes);   // [2][8 warps][1024]
+    __shared__ __align__(8) uint64_t full_bar[kPairStages];
+    constexpr int R = kPairR;
+    constexpr int kWarps = kNNThreads / 32;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int total_tiles = Mpad / kTilePoints;
+    const int tile0 = blockIdx.y * tiles_per_split;
+    int ntiles = total_tiles - tile0;
+    if (ntiles > tiles_per_split) ntiles = tiles_per_split;
+    if (ntiles <= 0) return;  // uniform per CTA
+    const float4* cand = Bp + (size_t)b * Mpad + (size_t)tile0 * kTilePoints;
+
+    if (tid == 0) {
+        for (int s = 0; s < kPairStages; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int pre = ntiles < kPairStages ? ntiles : kPairStages;
+        for (int s = 0; s < pre; ++s) {
+            mbar_arrive_expect_tx(&full_bar[s], kTileBytes);
+            tma_load_1d(tiles + (size_t)s * kTilePoints, cand + (size_t)s * kTilePoints, kTileBytes, &full_bar[s]);
+        }
+    }
+
+    const int row0 = blockIdx.x * (kNNThreads * R) + tid;
+    const float4* arow = A + (size_t)b * Npad;
+    float2 vx[R / 2], vy[R / 2], vz[R / 2], vn[R / 2];
+    float best[R];
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+        const float4 p = arow[row0 + r * kNNThreads], q = arow[row0 + (r + 1) * kNNThreads];
+        const float sc = FORM == 0 ? 1.0f : -2.0f;  // cdist: x1.mul(-2), exact
+        vx[r / 2] = make_float2(sc * p.x, sc * q.x);
+        vy[r / 2] = make_float2(sc * p.y, sc * q.y);
+        vz[r / 2] = make_float2(sc * p.z, sc * q.z);
+        vn[r / 2] = make_float2(p.w, q.w);
+        best[r] = best[r + 1] = __int_as_float(0x7f800000);
+    }
+
+    auto pair8 = [&](const float4& c, float (&d)[R]) {
+        const float2 cx = make_float2(c.x, c.x), cy = make_float2(c.y, c.y), cz = make_float2(c.z, c.z),
+                     cw = make_float2(c.w, c.w);
+#pragma unroll
+        for (int h = 0; h < R / 2; ++h) {
+            float2 o;
+            const float2 dot = __ffma2_rn(vz[h], cz, __ffma2_rn(vy[h], cy, __fmul2_rn(vx[h], cx)));
+            if (FORM == 0) {
+                o = __ffma2_rn(make_float2(-2.0f, -2.0f), dot, __fadd2_rn(vn[h], cw));  // (|a|^2 + |b|^2) + (-2 dot)
+            } else {
+                o = __fadd2_rn(__fadd2_rn(dot, vn[h]), cw);  // ATen _euclidean_dist: x1's norm first
+            }
+            d[2 * h] = o.x;
+            d[2 * h + 1] = o.y;
+        }
+    };
+    auto colmin8 = [&](const float (&d)[R]) -> unsigned int {
+        float m = fmin3(fmin3(d[0], d[1], d[2]), fmin3(d[3], d[4], d[5]), fminf(d[6], d[7]));
+        m = fmaxf(m, 0.0f);  // clamp(min=0) commutes with the minimum; makes the bits order like unsigned
+        return __reduce_min_sync(0xffffffffu, __float_as_uint(m));
+    };
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kPairStages;
+        mbar_wait(&full_bar[s], (uint32_t)((t / kPairStages) & 1));
+        const float4* tile = tiles + (size_t)s * kTilePoints;
+        unsigned int* strip = colw + ((size_t)(t & 1) * kWarps + warp) * kTilePoints;
+#pragma unroll 1
+        for (int jb = 0; jb < kTilePoints; jb += 32) {
+            unsigned int mine = 0x7f800000u;
+#pragma unroll 4
+            for (int jj = 0; jj < 32; jj += 2) {
+                float d0[R], d1[R];
+                pair8(tile[jb + jj], d0);
+                pair8(tile[jb + jj + 1], d1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) best[r] = fmin3(best[r], d0[r], d1[r]);
+                const unsigned int u0 = colmin8(d0), u1 = colmin8(d1);
+                if (lane == jj) mine = u0;
+                if (lane == jj + 1) mine = u1;
+            }
+            strip[jb + lane] = mine;
+        }
+        __syncthreads();  // all warps are done with stage s and have written their strips of parity (t & 1)
+        if (tid == 0 && t + kPairStages < ntiles) {
+            mbar_arrive_expect_tx(&full_bar[s], kTileBytes);
+            tma_load_1d(tiles + (size_t)s * kTilePoints, cand + (size_t)(t + kPairStages) * kTilePoints, kTileBytes,
+                        &full_bar[s]);
+        }
+        // merge the strips; strips of this parity are rewritten in tile t + 2, after the next __syncthreads
+        const unsigned int* base = colw + (size_t)(t & 1) * kWarps * kTilePoints;
+        const int jbase = (tile0 + t) * kTilePoints;
+        for (int q = tid; q < kTilePoints; q += kNNThreads) {
+            unsigned int v = base[q];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) v = min(v, base[w * kTilePoints + q]);
+            if (jbase + q < M) atomicMin(colmin_bits + (size_t)b * M + jbase + q, v);
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = row0 + r * kNNThreads;
+        if (i < N) atomicMin(rowmin_bits + (size_t)b * N + i, __float_as_uint(fmaxf(best[r], 0.0f)));
+    }
+}
+
+__global__ void nn_min_pair_init_kernel(unsigned int* a, size_t na, unsigned int* b, size_t nb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < na) a[i] = 0x7f800000u;
+    else if (i - na < nb) b[i - na] = 0x7f800000u;
+}
+__global__ void nn_min_pair_sqrt_kernel(float* a, size_t na, float* b, size_t nb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < na) a[i] = __fsqrt_rn(a[i]);
+    else if (i - na < nb) b[i - na] = __fsqrt_rn(b[i - na]);
+}
+
 // init: rowmin = +inf bits (or key = all ones)
 __global__ void nn_min_init_kernel(unsigned int* rowmin_bits, unsigned long long* rowkey, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,9 +348,9 @@ struct NNPlan {
     size_t off_a, off_b, off_key, total;
 };
 
-static NNPlan make_plan(int B, int N, int M) {
+static NNPlan make_plan(int B, int N, int M, int R = 4) {
     NNPlan p;
-    p.R = 4;
+    p.R = R;
     const int rows_per_cta = kNNThreads * p.R;
     p.Npad = (int)align_up(align_up((size_t)N, rows_per_cta), kTilePoints);
     p.Mpad = padded_points(M);
@@ -296,6 +438,55 @@ extern "C" int pcst_nn_min_f32(const float* a, const float* b, int B, int N, int
     if (st != PCST_OK) return st;
     if (rowarg || form != 0) {
         nn_min_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rowmin, rowarg, keys, n, form != 0);
+        PCST_CUDA(cudaGetLastError());
+    }
+    return PCST_OK;
+}
+
+
+extern "C" size_t pcst_nn_min_pair_workspace_bytes(int B, int N, int M) {
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    return make_plan(B, N, M, kPairR).total;
+}
+
+extern "C" int pcst_nn_min_pair_f32(const float* a, const float* b, int B, int N, int M, int form, float* rowmin,
+                                    float* colmin, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCST_CHECK_ARG(a && b && rowmin && colmin, "null pointer");
+    PCST_CHECK_ARG(B > 0 && N > 0 && M > 0, "B, N, M must be positive");
+    PCST_CHECK_ARG(B <= 65535, "B must be <= 65535");
+    PCST_CHECK_ARG(form == 0 || form == 1, "form must be 0 (loss) or 1 (cdist)");
+    const NNPlan p = make_plan(B, N, M, kPairR);
+    if (!ws || ws_bytes < p.total || ((uintptr_t)ws & 255)) {
+        set_error("pcst_nn_min_pair_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, p.total);
+        return PCST_ERR_WORKSPACE;
+    }
+    char* w = (char*)ws;
+    float4* A = (float4*)(w + p.off_a);
+    float4* Bp = (float4*)(w + p.off_b);
+    int st;
+    if ((st = launch_pack(a, B, N, p.Npad, A, stream)) != PCST_OK) return st;
+    if ((st = launch_pack(b, B, M, p.Mpad, Bp, stream)) != PCST_OK) return st;
+    const size_t na = (size_t)B * N, nb = (size_t)B * M;
+    nn_min_pair_init_kernel<<<(unsigned)((na + nb + 255) / 256), 256, 0, stream>>>((unsigned int*)rowmin, na,
+                                                                                    (unsigned int*)colmin, nb);
+    PCST_CUDA(cudaGetLastError());
+    const int smem = kPairStages * kTileBytes + 2 * (kNNThreads / 32) * kTilePoints * (int)sizeof(unsigned int);
+    dim3 grid(p.row_tiles, p.splits, B);
+    if (form == 0) {
+        auto kern = nn_min_pair_kernel<0>;
+        PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, kNNThreads, smem, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, p.tiles_per_split, (unsigned int*)rowmin,
+                                                 (unsigned int*)colmin);
+    } else {
+        auto kern = nn_min_pair_kernel<1>;
+        PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, kNNThreads, smem, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, p.tiles_per_split, (unsigned int*)rowmin,
+                                                 (unsigned int*)colmin);
+    }
+    PCST_CUDA(cudaGetLastError());
+    if (form != 0) {
+        nn_min_pair_sqrt_kernel<<<(unsigned)((na + nb + 255) / 256), 256, 0, stream>>>(rowmin, na, colmin, nb);
         PCST_CUDA(cudaGetLastError());
     }
     return PCST_OK;

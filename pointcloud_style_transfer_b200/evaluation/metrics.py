@@ -21,17 +21,15 @@ class PointCloudMetrics:
 
     def chamfer_distance(self, pred: torch.Tensor, target: torch.Tensor, bidirectional: bool = True) -> torch.Tensor:
         """evaluation/metrics.py:20-44: Euclidean (un-squared) NN distances of torch.cdist, (mean+mean)/2."""
+        if bidirectional:  # rows and columns of the same cdist matrix: one sweep
+            d1, d2 = ops.nn_min_pair(pred, target, 1)
+            return (torch.mean(d1, dim=1) + torch.mean(d2, dim=1)) / 2
         d1, _ = ops.nn_min(pred, target, 1, False)
-        c1 = torch.mean(d1, dim=1)
-        if bidirectional:
-            d2, _ = ops.nn_min(target, pred, 2, False)
-            return (c1 + torch.mean(d2, dim=1)) / 2
-        return c1
+        return torch.mean(d1, dim=1)
 
     def hausdorff_distance(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """evaluation/metrics.py:90-105."""
-        d1, _ = ops.nn_min(pred, target, 1, False)
-        d2, _ = ops.nn_min(target, pred, 2, False)
+        d1, d2 = ops.nn_min_pair(pred, target, 1)
         return torch.max(torch.max(d1, dim=1)[0], torch.max(d2, dim=1)[0])
 
     def coverage_score(self, pred: torch.Tensor, target: torch.Tensor, threshold: float = 0.01) -> float:

@@ -50,9 +50,9 @@ def _workspace(nbytes: int, device) -> Tensor:
 
 # Launch accounting and optional per-op CUDA-event timing (used by bench.py for `gpu_launches` and the
 # roofline's live kernel durations).  KERNELS_PER_CALL counts __global__ launches (memsets excluded).
-KERNELS_PER_CALL = {"pcst_fps_f32": 1, "pcst_ball_query_f32": 3, "pcst_square_distance_f32": 1,
+KERNELS_PER_CALL = {"pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
-                    "pcst_sa_mlp_max_f32": 3, "pcst_nn_min_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
+                    "pcst_sa_mlp_max_f32": 3, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
                     "pcst_knn_interpolate_f32": 1}
 launch_count = 0
 _event_log = None  # None = off; else list of (name, start_event, end_event)
@@ -329,6 +329,30 @@ def _(a, b, form, want_arg):
     return a.new_empty(B, N, dtype=torch.float32), a.new_empty((B, N) if want_arg else (0,), dtype=torch.int64)
 
 
+@torch.library.custom_op("pcst::nn_min_pair", mutates_args=(), device_types="cuda")
+def nn_min_pair(a: Tensor, b: Tensor, form: int) -> Tuple[Tensor, Tensor]:
+    """Row AND column minima of the pair matrix between a [B,N,3] and b [B,M,3] in one sweep (every pair is
+    evaluated once; the second direction's matrix is exactly the transpose).  form 0 = loss form,
+    form 1 = cdist (a = x1).  -> (rowmin [B,N], colmin [B,M]), bit-identical to two ``nn_min`` calls."""
+    lib = _lib.load()
+    _need_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    rowmin = torch.empty(B, N, dtype=torch.float32, device=a.device)
+    colmin = torch.empty(B, M, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        ws = _workspace(lib.pcst_nn_min_pair_workspace_bytes(B, N, M), a.device)
+        _call("pcst_nn_min_pair_f32", _p(a), _p(b), B, N, M, form, _p(rowmin), _p(colmin), _p(ws), ws.numel(), _stream())
+    return rowmin, colmin
+
+
+@nn_min_pair.register_fake
+def _(a, b, form):
+    return (a.new_empty(a.shape[0], a.shape[1], dtype=torch.float32),
+            a.new_empty(b.shape[0], b.shape[1], dtype=torch.float32))
+
+
 @torch.library.custom_op("pcst::chamfer_bwd", mutates_args=(), device_types="cuda")
 def chamfer_bwd(pred: Tensor, target: Tensor, arg_pt: Tensor, arg_tp: Tensor, grad_out: Tensor) -> Tuple[Tensor, Tensor]:
     lib = _lib.load()
@@ -355,10 +379,12 @@ class _ChamferLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
         need_grad = pred.requires_grad or target.requires_grad
-        d1, a1 = nn_min(pred, target, 0, need_grad)
-        d2, a2 = nn_min(target, pred, 0, need_grad)
-        if need_grad:
+        if need_grad:  # the backward needs both argmins: two one-directional sweeps with index tracking
+            d1, a1 = nn_min(pred, target, 0, True)
+            d2, a2 = nn_min(target, pred, 0, True)
             ctx.save_for_backward(pred, target, a1, a2)
+        else:          # values only: one sweep serves both directions
+            d1, d2 = nn_min_pair(pred, target, 0)
         return d1.mean(dim=1) + d2.mean(dim=1)
 
     @staticmethod

@@ -409,6 +409,42 @@ def test_nn_min_120k_rows_subset_and_properties(api, dev, oracle):
     assert torch.equal(sub, d1[:, 5000:6000])
 
 
+@pytest.mark.parametrize("B,N,M", [(2, 4096, 3900), (1, 1, 5), (1, 5, 1), (3, 1025, 1023), (2, 2049, 7777),
+                                   (1, 30000, 30000)])
+def test_nn_min_pair_one_sweep_matches_oracle_both_directions(api, dev, oracle, B, N, M):
+    """Row and column minima from ONE sweep (each pair evaluated once) equal the oracle's two
+    one-directional evaluations bit for bit -- loss form and cdist form."""
+    a, b = S.uniform_cloud(11, B, N).numpy(), S.uniform_cloud(21, B, M).numpy()
+    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    r0, c0 = api.ops.nn_min_pair(ta, tb, 0)
+    assert np.array_equal(bits(r0.cpu().numpy()), bits(oracle.nn_min(a, b, 0)))
+    assert np.array_equal(bits(c0.cpu().numpy()), bits(oracle.nn_min(b, a, 0)))
+    r1, c1 = api.ops.nn_min_pair(ta, tb, 1)
+    assert np.array_equal(bits(r1.cpu().numpy()), bits(oracle.nn_min(a, b, 1)))
+    assert np.array_equal(bits(c1.cpu().numpy()), bits(oracle.nn_min(b, a, 2)))
+
+
+def test_nn_min_pair_golden_lattice_and_120k_equals_two_sweeps(api, dev, golden):
+    g = golden("c1_chamfer")
+    p, t = torch.from_numpy(g["pred"]).to(dev), torch.from_numpy(g["target"]).to(dev)
+    r, c = api.ops.nn_min_pair(p, t, 0)
+    assert np.array_equal(bits(r.cpu().numpy()), bits(g["loss_rowmin"]))   # the reference's own minima
+    assert np.array_equal(bits(c.cpu().numpy()), bits(g["loss_colmin"]))
+    gl = golden("lattice")
+    x, y = torch.from_numpy(gl["x"]).to(dev), torch.from_numpy(gl["y"]).to(dev)
+    r, c = api.ops.nn_min_pair(x, y, 0)
+    assert np.array_equal(bits(r.cpu().numpy()), bits(gl["loss_rowmin"]))
+    assert np.array_equal(bits(c.cpu().numpy()), bits(gl["loss_colmin"]))
+    # full size: the single sweep against the two one-directional sweeps (themselves oracle-checked above)
+    a, b = S.lidar_scan(0).to(dev), S.lidar_scan(1).to(dev)
+    r, c = api.ops.nn_min_pair(a, b, 0)
+    assert torch.equal(r, api.ops.nn_min(a, b, 0, False)[0])
+    assert torch.equal(c, api.ops.nn_min(b, a, 0, False)[0])
+    r, c = api.ops.nn_min_pair(a, b, 1)
+    assert torch.equal(r, api.ops.nn_min(a, b, 1, False)[0])
+    assert torch.equal(c, api.ops.nn_min(b, a, 2, False)[0])
+
+
 def test_nn_min_lattice_order_independent(api, dev, golden):
     g = golden("lattice")
     x, y = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)
