@@ -151,7 +151,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mlp-precision", type=int, default=int(os.environ.get("PCST_MLP_PRECISION", "0")))
+    ap.add_argument("--mlp-precision", type=int, default=int(os.environ.get("PCST_MLP_PRECISION", "1")),
+                    help="1 = bf16 tcgen05 shared MLP (north_star's design, default); 0 = fp32 CUDA-core MLP")
     ap.add_argument("--chamfer-steps", type=int, default=5)
     args = ap.parse_args()
 
@@ -275,15 +276,17 @@ def main():
         fps_gbs = fps_bytes / (fps_ms_max * 1e-3) / 1e9
         pairs = 2.0 * N_POINTS * N_POINTS               # both directions, as the reference evaluates them
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s, FP32 CUDA cores
-        ch_tflops = 8.0 * pairs / (t_ch * 1e-3) / 1e12
+        # one sweep serves both directions (the second matrix is the exact transpose): N*M unique pair evaluations
+        ch_tflops = 8.0 * (pairs / 2) / (t_ch * 1e-3) / 1e12
         line = {
             "metric": "SA points/sec (PointNet2Encoder fwd, 120k-pt scan)", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mlp_precision == 0 else "f32 distances, bf16 MLP",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mlp_precision == 0 else "f32 distances/indices, bf16 tcgen05 MLP (f32 accumulate)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "points": N_POINTS, "feature_dim": FEATURE_DIM,
                        "scans_per_gpu": 1, "l2": "flushed between timed iterations (256 MiB write)",
-                       "launch": "one CUDA-graph replay per step", "mlp_precision": args.mlp_precision},
+                       "launch": "one CUDA-graph replay per step (stage-2 sampling on a parallel graph branch)",
+                       "mlp_precision": args.mlp_precision},
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": t_e2e,
                     "h2d_bytes_per_step": int(scan.numel() * 4 + 16), "d2h_bytes_per_step": FEATURE_DIM * 4},
             "gpu_launches": launches_per_step * K * 2,
@@ -294,9 +297,11 @@ def main():
             "op_ms_eager": op_ms,
             "chamfer": {"metric": "Chamfer NN pairs/sec (120k x 120k, both directions)", "value": world * pairs / (t_ch * 1e-3),
                         "unit": "pairs/s", "ms_per_call": t_ch,
-                        "roofline": {"kernel": "nn_min_kernel", "bound": "fp32", "achieved": ch_tflops, "peak": fp32_peak,
+                        "roofline": {"kernel": "nn_min_pair_kernel<0>", "bound": "fp32", "achieved": ch_tflops, "peak": fp32_peak,
                                      "unit": "TFLOP/s", "frac": ch_tflops / fp32_peak,
-                                     "model": "8 flop per pair evaluation; peak = 148 SMs x 128 lanes x 2 x sm_max_mhz"}},
+                                     "model": "8 flop per UNIQUE pair evaluation (N*M: one sweep yields both directions' minima); "
+                                              "peak = 148 SMs x 128 lanes x 2 x sm_max_mhz (computed, not measured)",
+                                     "frac_if_both_directions_counted": 2 * ch_tflops / fp32_peak}},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -94,26 +94,37 @@ int pcst_group_f32(const float* xyz, const float* feats, const float* new_xyz, c
                    int B, int N, int S, int K, int D, float* out, pcst_stream_t stream);
 
 /* ---- SetAbstraction.apply_mlp: models/pointnet2_encoder.py:106-112 (eval-mode BatchNorm) --------
- * Fused grouping gather + 3 x relu(bn(conv1x1(.))) + max over the K samples of each group.
- *   xyz [B,N,3], feats [B,N,D] or NULL, new_xyz [B,S,3] or NULL, idx [B,S,K] int64 or NULL.
- *   idx == NULL means group_all (:81-89): S = 1, K = N, the "group" is the whole cloud in order and
- *   no centroid is subtracted.
- * Layer l (l = 0..2): weight w[l] [Cout_l, Cin_l] fp32 row-major (the Conv2d weight [Cout,Cin,1,1]),
+ * Fused grouping gather (:94-101) + 3 x relu(bn(conv1x1(.))) + max over the K samples of each group.
+ *
+ * Parameters are PACKED ONCE per parameter version and reused by every forward:
+ *   layer l (l = 0..2): weight w[l] [Cout_l, Cin_l] fp32 row-major (the Conv2d weight [Cout,Cin,1,1]),
  *   scale[l], shift[l] [Cout_l]: y = relu(scale * (w . x) + shift), i.e. conv bias and eval-mode BN
  *   folded by the caller: scale = gamma / sqrt(var + eps), shift = (bias - mean) * scale + beta.
- *   Cin_0 = 3 + D, Cin_l = Cout_{l-1}.  Supported: Cout_l multiple of 32, Cout_l <= 1024.
- * out [B, Cout_2, S] (channel-first, the reference's layout).
- * precision: 0 = fp32 CUDA-core path; 1 = bf16 tcgen05/TMEM tensor-core path (fp32 accumulate). */
+ *   Cin_0 = 3 + D, Cin_l = Cout_{l-1}.  Supported: Cout_l a multiple of 32, Cout_l <= 1024.
+ * precision: 0 = fp32 CUDA-core path; 1 = bf16 tcgen05/TMEM tensor-core path (fp32 accumulate; needs
+ *   Cout_0 <= 256 and Cout_1, Cout_2 <= 512, otherwise the fp32 path is used).  pcst_sa_mlp_pack_f32
+ *   writes the layout the chosen path wants (tensor cores: bf16 K-major UMMA operand blocks + fp32
+ *   scale/shift) into `packed` (caller-owned, 256-byte aligned, pcst_sa_mlp_packed_bytes() bytes).
+ *
+ * pcst_sa_mlp_max_f32:
+ *   xyz [B,N,3], feats [B,N,D] or NULL, new_xyz [B,S,3] or NULL, idx [B,S,K] int64 (clamped) or NULL.
+ *   idx == NULL means group_all (:81-89): S = 1, K = N, the "group" is the whole cloud in order and
+ *   no centroid is subtracted.  cout/precision/D must be the ones `packed` was built with.
+ * out [B, S, Cout_2] POINT-major; the reference's channel-first [B, Cout_2, S] is out.permute(0, 2, 1)
+ * (the next stage consumes the point-major form, models/pointnet2_encoder.py:128-129). */
 typedef struct {
     const float* w[3];
     const float* scale[3];
     const float* shift[3];
     int cout[3];
 } pcst_mlp3_t;
-size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp, int precision);
+size_t pcst_sa_mlp_packed_bytes(int D, const int* cout /*[3]*/, int precision);
+int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision, void* packed, size_t packed_bytes,
+                         pcst_stream_t stream);
+size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision);
 int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
-                        int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp, int precision,
-                        float* out, void* ws, size_t ws_bytes, pcst_stream_t stream);
+                        int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision,
+                        const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream);
 
 /* ---- nearest-neighbour minimum reduction ------------------------------------------------------
  * a [B,N,3], b [B,M,3] -> rowmin [B,N] = min_j D(a_i, b_j), rowarg [B,N] (optional, may be NULL) =

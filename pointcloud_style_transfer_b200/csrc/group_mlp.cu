@@ -5,7 +5,9 @@
 // precision 0 (this file): one tiled fp32 SGEMM-style launch per layer; layer 0 gathers its rows
 // on the fly (the grouped [B,S,K,3+D] tensor is never written), the last layer reduces the max over
 // each group's K rows in its epilogue (atomicMax on the IEEE bits of post-ReLU values, which are
-// >= +0).  Intermediate activations (rows x C fp32, a few MB) round-trip through L2.
+// >= +0).  Intermediate activations (rows x C fp32, a few MB) round-trip through L2.  Stages with few
+// rows (the group_all stage: 128 rows per scan) use 32 x 32 tiles so that the launch still covers
+// dozens of SMs.
 // precision 1 (tcgen05 bf16 tensor-core chain) lives in sa_mlp_tc.cu.
 //
 // Bound: the dense contraction is tensor-core work; this fp32 path exists as the exact-parity
@@ -14,8 +16,6 @@
 
 namespace pcst {
 
-constexpr int kMT = 64;   // rows per CTA tile
-constexpr int kNT = 64;   // output channels per CTA tile
 constexpr int kKC = 16;   // reduction chunk
 constexpr int kMlpThreads = 256;
 
@@ -59,27 +59,32 @@ __device__ __forceinline__ float load_x(const LayerArgs& a, int row, int ci) {
     return a.feats[((size_t)b * a.N + j) * a.D + (ci - 3)];
 }
 
+// T x T output tile per CTA (T = 64: 4 x 4 register micro-tile per thread; T = 32: 2 x 2), 256 threads.
+template <int T>
 __global__ void __launch_bounds__(kMlpThreads)
 mlp_layer_kernel(const LayerArgs a) {
-    __shared__ __align__(16) float Xs[kKC][kMT + 4];
-    __shared__ __align__(16) float Ws[kKC][kNT + 4];
-    __shared__ float Ys[kMT][kNT + 1];
+    constexpr int MI = T / 16;  // micro-tile edge
+    __shared__ __align__(16) float Xs[kKC][T + 4];
+    __shared__ __align__(16) float Ws[kKC][T + 4];
+    __shared__ float Ys[T][T + 1];
 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    const int row0 = blockIdx.x * kMT;
-    const int col0 = blockIdx.y * kNT;
-    float acc[4][4];
+    const int row0 = blockIdx.x * T;
+    const int col0 = blockIdx.y * T;
+    float acc[MI][MI];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < MI; ++j) acc[i][j] = 0.f;
 
-    const int lr = tid >> 2;         // 0..63: row (X) / channel (W) loaded by this thread
-    const int lc = (tid & 3) * 4;    // 0,4,8,12: first ci of the 4 it loads
+    // loader: T rows x 16 reduction columns of X and of W per chunk, T * 16 / 256 elements per thread
+    constexpr int LPT = T * kKC / kMlpThreads;  // 4 (T = 64) or 2 (T = 32)
+    const int lr = tid / (kKC / LPT);            // row (X) / channel (W) loaded by this thread
+    const int lc = (tid % (kKC / LPT)) * LPT;    // first ci of the LPT it loads
     for (int k0 = 0; k0 < a.Cin; k0 += kKC) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LPT; ++u) {
             const int ci = k0 + lc + u;
             Xs[lc + u][lr] = load_x(a, row0 + lr, ci);
             const int co = col0 + lr;
@@ -88,49 +93,52 @@ mlp_layer_kernel(const LayerArgs a) {
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < kKC; ++kk) {
-            const float4 xv = *reinterpret_cast<const float4*>(&Xs[kk][ty * 4]);
-            const float4 wv = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
-            const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+            float xr[MI], wr[MI];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i) {
+                xr[i] = Xs[kk][ty * MI + i];
+                wr[i] = Ws[kk][tx * MI + i];
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(xr[i], wr[j], acc[i][j]);
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < MI; ++j) acc[i][j] = __fmaf_rn(xr[i], wr[j], acc[i][j]);
         }
         __syncthreads();
     }
 
     // epilogue: y = relu(scale * acc + shift)
-    float sc[4], sh[4];
+    float sc[MI], sh[MI];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int co = col0 + tx * 4 + j;
+    for (int j = 0; j < MI; ++j) {
+        const int co = col0 + tx * MI + j;
         sc[j] = co < a.Cout ? a.scale[co] : 0.f;
         sh[j] = co < a.Cout ? a.shift[co] : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = row0 + ty * 4 + i;
+    for (int i = 0; i < MI; ++i) {
+        const int row = row0 + ty * MI + i;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < MI; ++j) {
             const float y = __fmaf_rn(acc[i][j], sc[j], sh[j]);
             const float v = y > 0.f ? y : 0.f;
             if (a.pool) {
-                Ys[ty * 4 + i][tx * 4 + j] = v;
-            } else if (row < a.rows && col0 + tx * 4 + j < a.Cout) {
-                a.Y[(size_t)row * a.Cout + col0 + tx * 4 + j] = v;
+                Ys[ty * MI + i][tx * MI + j] = v;
+            } else if (row < a.rows && col0 + tx * MI + j < a.Cout) {
+                a.Y[(size_t)row * a.Cout + col0 + tx * MI + j] = v;
             }
         }
     }
     if (!a.pool) return;
     __syncthreads();
-    // max over the rows of each group segment inside this tile, one (segment, channel) per thread
-    int rend = row0 + kMT;
+    // max over the rows of each group segment inside this tile, one (segment, channel) per thread;
+    // pooled rows are point-major: out[(b * S + s), co]
+    int rend = row0 + T;
     if (rend > a.rows) rend = a.rows;
     const int g0 = row0 / a.K, g1 = (rend - 1) / a.K;
     const int nseg = g1 - g0 + 1;
-    for (int item = tid; item < nseg * kNT; item += kMlpThreads) {
-        const int seg = item / kNT, c = item % kNT;
+    for (int item = tid; item < nseg * T; item += kMlpThreads) {
+        const int seg = item / T, c = item % T;
         const int co = col0 + c;
         if (co >= a.Cout) continue;
         const int g = g0 + seg;
@@ -139,64 +147,113 @@ mlp_layer_kernel(const LayerArgs a) {
         if (rb > rend) rb = rend;
         float m = 0.f;
         for (int r = ra; r < rb; ++r) m = fmaxf(m, Ys[r - row0][c]);
-        const int b = g / a.S, s = g % a.S;
-        atomicMax(a.out_bits + ((size_t)b * a.Cout + co) * a.S + s, __float_as_uint(m));
+        atomicMax(a.out_bits + (size_t)g * a.Cout + co, __float_as_uint(m));
     }
 }
 
-int sa_mlp_max_tc(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
-                  int K, int D, const pcst_mlp3_t* mlp, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
-size_t sa_mlp_max_tc_workspace(int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp);
-bool sa_mlp_max_tc_supported(int D, const pcst_mlp3_t* mlp);
+bool sa_mlp_tc_supported(int D, const int* cout);
+size_t sa_mlp_tc_blob_bytes(int D, const int* cout);
+int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, void* blob, cudaStream_t stream);
+int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
+                  int K, int D, const int* cout, const void* blob, float* out, cudaStream_t stream);
+
+// fp32 blob: w0 [n0, 3+D] | w1 [n1, n0] | w2 [n2, n1] | scale0 shift0 scale1 shift1 scale2 shift2, each 256-byte aligned
+struct F32Blob {
+    size_t w[3], scale[3], shift[3], total;
+};
+static F32Blob f32_blob(int D, const int* cout) {
+    F32Blob b;
+    size_t off = 0;
+    int cin = 3 + D;
+    for (int l = 0; l < 3; ++l) {
+        b.w[l] = off;
+        off += align_up((size_t)cout[l] * cin * sizeof(float), 256);
+        cin = cout[l];
+    }
+    for (int l = 0; l < 3; ++l) {
+        b.scale[l] = off;
+        off += align_up((size_t)cout[l] * sizeof(float), 256);
+        b.shift[l] = off;
+        off += align_up((size_t)cout[l] * sizeof(float), 256);
+    }
+    b.total = off;
+    return b;
+}
 
 }  // namespace pcst
 
 using namespace pcst;
 
-static int check_mlp(const pcst_mlp3_t* mlp) {
-    if (!mlp) return 0;
-    for (int l = 0; l < 3; ++l) {
-        if (!mlp->w[l] || !mlp->scale[l] || !mlp->shift[l]) return 0;
-        if (mlp->cout[l] <= 0 || mlp->cout[l] > 1024 || (mlp->cout[l] % 32) != 0) return 0;
-    }
+static int check_cout(const int* cout) {
+    if (!cout) return 0;
+    for (int l = 0; l < 3; ++l)
+        if (cout[l] <= 0 || cout[l] > 1024 || (cout[l] % 32) != 0) return 0;
     return 1;
 }
+// the tensor-core kernel covers widths up to 512 with the first layer <= 256; anything else runs on the
+// fp32 path, which is the more precise of the two
+static bool use_tc(int D, const int* cout, int precision) { return precision == 1 && sa_mlp_tc_supported(D, cout); }
 
-extern "C" size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp,
-                                                  int precision) {
-    if (B <= 0 || N <= 0 || S <= 0 || K <= 0 || D < 0 || !check_mlp(mlp)) return 0;
-    // stages whose layers do not fit the tensor-core kernel (Cout > 256: the tiny group_all stage) run
-    // on the fp32 path, which is the more precise of the two
-    if (precision == 1 && sa_mlp_max_tc_supported(D, mlp)) return sa_mlp_max_tc_workspace(B, N, S, K, D, mlp);
+extern "C" size_t pcst_sa_mlp_packed_bytes(int D, const int* cout, int precision) {
+    if (D < 0 || !check_cout(cout)) return 0;
+    return use_tc(D, cout, precision) ? sa_mlp_tc_blob_bytes(D, cout) : f32_blob(D, cout).total;
+}
+
+extern "C" int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision, void* packed, size_t packed_bytes,
+                                    pcst_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCST_CHECK_ARG(mlp && packed, "null pointer");
+    PCST_CHECK_ARG(D >= 0 && check_cout(mlp->cout), "Cout must be a multiple of 32 in [32, 1024]");
+    for (int l = 0; l < 3; ++l) PCST_CHECK_ARG(mlp->w[l] && mlp->scale[l] && mlp->shift[l], "null layer pointer");
+    PCST_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16 tensor cores)");
+    PCST_CHECK_ARG(packed_bytes >= pcst_sa_mlp_packed_bytes(D, mlp->cout, precision) && ((uintptr_t)packed & 255) == 0,
+                   "packed buffer too small or not 256-byte aligned");
+    if (use_tc(D, mlp->cout, precision)) return sa_mlp_tc_pack(mlp, D, packed, stream);
+    const F32Blob b = f32_blob(D, mlp->cout);
+    int cin = 3 + D;
+    for (int l = 0; l < 3; ++l) {
+        const size_t n = (size_t)mlp->cout[l];
+        PCST_CUDA(cudaMemcpyAsync((char*)packed + b.w[l], mlp->w[l], n * cin * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        PCST_CUDA(cudaMemcpyAsync((char*)packed + b.scale[l], mlp->scale[l], n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        PCST_CUDA(cudaMemcpyAsync((char*)packed + b.shift[l], mlp->shift[l], n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        cin = mlp->cout[l];
+    }
+    return PCST_OK;
+}
+
+extern "C" size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const int* cout, int precision) {
+    if (B <= 0 || N <= 0 || S <= 0 || K <= 0 || D < 0 || !check_cout(cout)) return 0;
+    if (use_tc(D, cout, precision)) return 0;  // activations stay in shared memory / TMEM
     const size_t rows = (size_t)B * S * K;
-    return align_up(rows * mlp->cout[0] * sizeof(float), 256) + align_up(rows * mlp->cout[1] * sizeof(float), 256);
+    return align_up(rows * cout[0] * sizeof(float), 256) + align_up(rows * cout[1] * sizeof(float), 256);
 }
 
 extern "C" int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
-                                   int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp, int precision,
-                                   float* out, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
+                                   int B, int N, int S, int K, int D, const int* cout, int precision,
+                                   const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    PCST_CHECK_ARG(xyz && out, "null pointer");
+    PCST_CHECK_ARG(xyz && out && packed, "null pointer");
     PCST_CHECK_ARG(B > 0 && N > 0 && S > 0 && K > 0 && D >= 0, "bad sizes");
     PCST_CHECK_ARG(D == 0 || feats, "feats is NULL but D > 0");
-    PCST_CHECK_ARG(check_mlp(mlp), "mlp: null pointers, or Cout not a multiple of 32 in [32, 1024]");
+    PCST_CHECK_ARG(check_cout(cout), "Cout must be a multiple of 32 in [32, 1024]");
     PCST_CHECK_ARG(idx || (S == 1 && K == N && !new_xyz), "idx == NULL means group_all: S = 1, K = N, new_xyz = NULL");
     PCST_CHECK_ARG(!idx || new_xyz, "new_xyz is required with idx");
     PCST_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16 tensor cores)");
-    const size_t need = pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, mlp, precision);
+    PCST_CHECK_ARG(((uintptr_t)packed & 255) == 0, "packed must be 256-byte aligned");
+    if (use_tc(D, cout, precision)) return sa_mlp_tc_run(xyz, feats, new_xyz, idx, B, N, S, K, D, cout, packed, out, stream);
+
+    const size_t need = pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, cout, precision);
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 255)) {
         set_error("pcst_sa_mlp_max_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need);
         return PCST_ERR_WORKSPACE;
     }
-    if (precision == 1 && sa_mlp_max_tc_supported(D, mlp))
-        return sa_mlp_max_tc(xyz, feats, new_xyz, idx, B, N, S, K, D, mlp, out, ws, ws_bytes, stream);
-
     const size_t rows_sz = (size_t)B * S * K;
     PCST_CHECK_ARG(rows_sz < (1u << 30), "B*S*K too large");
     const int rows = (int)rows_sz;
+    const F32Blob blob = f32_blob(D, cout);
     float* act0 = (float*)ws;
-    float* act1 = (float*)((char*)ws + align_up(rows_sz * mlp->cout[0] * sizeof(float), 256));
-    PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * mlp->cout[2] * S * sizeof(float), stream));
+    float* act1 = (float*)((char*)ws + align_up(rows_sz * cout[0] * sizeof(float), 256));
+    PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * cout[2] * sizeof(float), stream));
 
     LayerArgs a = {};
     a.xyz = xyz; a.feats = feats; a.new_xyz = new_xyz; a.idx = idx;
@@ -204,16 +261,24 @@ extern "C" int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const f
     a.rows = rows;
     int cin = 3 + D;
     const float* x_in = nullptr;
+    const bool small = rows <= 2048;  // few rows: smaller tiles so that the layer still spreads over many SMs
     for (int l = 0; l < 3; ++l) {
         a.gather = (l == 0);
         a.X = x_in;
-        a.W = mlp->w[l]; a.scale = mlp->scale[l]; a.shift = mlp->shift[l];
-        a.Cin = cin; a.Cout = mlp->cout[l];
+        a.W = (const float*)((const char*)packed + blob.w[l]);
+        a.scale = (const float*)((const char*)packed + blob.scale[l]);
+        a.shift = (const float*)((const char*)packed + blob.shift[l]);
+        a.Cin = cin; a.Cout = cout[l];
         a.pool = (l == 2);
         a.Y = l == 0 ? act0 : act1;
         a.out_bits = (unsigned int*)out;
-        dim3 grid((rows + kMT - 1) / kMT, (a.Cout + kNT - 1) / kNT);
-        mlp_layer_kernel<<<grid, kMlpThreads, 0, stream>>>(a);
+        if (small) {
+            dim3 grid((rows + 31) / 32, (a.Cout + 31) / 32);
+            mlp_layer_kernel<32><<<grid, kMlpThreads, 0, stream>>>(a);
+        } else {
+            dim3 grid((rows + 63) / 64, (a.Cout + 63) / 64);
+            mlp_layer_kernel<64><<<grid, kMlpThreads, 0, stream>>>(a);
+        }
         PCST_CUDA(cudaGetLastError());
         x_in = a.Y;
         cin = a.Cout;

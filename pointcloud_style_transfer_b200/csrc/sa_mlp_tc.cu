@@ -2,23 +2,24 @@
 //
 // Replaces index_points x2 + subtract + cat + apply_mlp (models/pointnet2_encoder.py:94-112, eval
 // mode) with ONE kernel per set-abstraction stage: gather -> 3 x (GEMM, scale/shift, ReLU) -> max.
-// A CTA owns a tile of 128 rows (rows = (b, s, k) flattened = 4 groups of K=32, 2 of K=64, ...).
-//   * layer-0 input rows are gathered from HBM (xyz - centroid, features), converted to bf16 and laid
-//     out in shared memory as the K-major, no-swizzle UMMA operand [Kp/8][128 rows][8] (one 8x16-byte
-//     core matrix = 128 contiguous bytes; SBO = 128 B between 8-row groups, LBO = 2048 B between
-//     K chunks);
-//   * the three weight matrices are pre-packed once per call to bf16 [Kp/8][Cout][8] (same canonical
-//     layout) and brought in by one 1-D TMA bulk copy each, all resident for the CTA's lifetime;
-//   * each layer is Kp/16 tcgen05.mma (M=128, N=Cout, K=16, bf16 x bf16 -> fp32) issued by one thread,
-//     accumulating in TMEM (128 lanes x Cout columns); completion is signalled with tcgen05.commit on
-//     an mbarrier;
-//   * the epilogue reads the accumulator with tcgen05.ld (32 lanes x 16 columns per warp-instruction),
-//     applies the folded conv-bias/BatchNorm scale+shift and ReLU in fp32, and either writes the next
-//     layer's bf16 operand straight back into shared memory in the canonical layout, or (last layer)
-//     reduces the max over each group's rows with REDUX and merges across warps/CTAs with atomicMax on
-//     the IEEE bits (post-ReLU values are >= +0).
-// Activations never touch HBM.  Bound: tensor pipe in the limit of many rows; at the reference's
-// shapes (16 384 / 8 192 rows per scan) the stage is latency-bound.
+// A CTA owns a tile of 128 rows (rows = (b, s, k) flattened = 4 groups of K=32, 2 of K=64, ...) and
+// runs a short table of GEMM steps over it.  Warp roles (192 threads):
+//   warps 0-3  gather the layer-0 rows from HBM (features with 128-bit loads, then xyz - centroid) into
+//              shared memory as the bf16 K-major no-swizzle UMMA operand [Kp/8][128 rows][8], later run the epilogues: read
+//              the fp32 accumulator from TMEM (tcgen05.ld 32x32b, warp w owns lanes 32w..32w+31), apply the
+//              folded conv-bias / BatchNorm scale+shift and ReLU, and either write the next step's bf16
+//              operand back to shared memory or reduce the max over each group's rows;
+//   warp 4     allocates TMEM; its lane 0 streams the pre-packed bf16 weights [Kp/8][N][8] through a
+//              ring of shared-memory stages in 32-row K chunks with 1-D TMA bulk copies (UBLKCP),
+//              running ahead of the math across steps (weights do not depend on data);
+//   warp 5     lane 0 issues the tcgen05.mma (M=128, N<=256, K=16, bf16 x bf16 -> fp32 in TMEM), frees
+//              ring stages and signals accumulator completion with tcgen05.commit -> mbarrier.
+// Layers wider than 256 (the group_all stage: 259 -> 256 -> 512 -> F) are cut into N halves whose
+// outputs feed the next layer as K halves accumulating into the same TMEM columns, so the widest
+// operand in shared memory stays 128 x 272 bf16 and the accumulators fit the 512 TMEM columns.
+// Activations never touch HBM; weights are packed ONCE per parameter version (pcst_sa_mlp_pack_f32)
+// and cached by the caller.  Bound: tensor pipe in the limit of many rows; at the reference's shapes
+// (16 384 / 8 192 / 128 rows per scan) a stage is latency-bound.
 // Precision: bf16 operands, fp32 accumulate/epilogue -> features within rtol 2e-2 / atol 2e-2 of
 // the reference's fp32 result.
 #include <cuda_bf16.h>
@@ -27,17 +28,26 @@
 
 namespace pcst {
 
-constexpr int kTcM = 128;        // rows per CTA = TMEM lanes
-constexpr int kTcThreads = 128;  // 4 warps: warp w owns TMEM lanes [32w, 32w+32)
-constexpr int kTcMaxN = 256;     // one tcgen05.mma covers the whole layer width
+constexpr int kTcM = 128;           // rows per CTA = TMEM lanes
+constexpr int kTcEpiThreads = 128;  // warps 0-3
+constexpr int kTcThreads = 192;     // + producer warp + MMA warp
+constexpr int kTcMaxN = 256;        // one tcgen05.mma covers a whole step's width
+constexpr int kTcChunkK = 32;       // K rows per ring stage
+constexpr int kTcMaxStages = 4;
+constexpr int kTcMaxSteps = 9;
+constexpr int kTcMaxBlocks = 7;
 
-struct TcLayer {
-    const __nv_bfloat16* w;  // packed [kp/8][n][8]
-    const float* scale;
-    const float* shift;
-    int kp;  // padded reduction length (multiple of 16)
-    int n;   // output channels (multiple of 32, <= 256)
-    uint32_t smem_off;  // byte offset of the weights inside dynamic shared memory
+struct TcStep {
+    uint32_t a_off;     // shared-memory offset of the A operand
+    uint32_t out_off;   // epi 1: shared-memory offset of the activation buffer written
+    uint32_t w_off;     // offset of this step's weight block in the packed blob
+    uint16_t kp;        // reduction length (multiple of 16)
+    uint16_t n;         // output channels of the step (multiple of 16, <= 256)
+    uint16_t tmem_col;  // first accumulator column
+    uint16_t out_c0;    // epi 2: first output channel
+    uint16_t ss_idx;    // first channel in the scale/shift tables
+    uint8_t acc;        // accumulate onto the TMEM contents
+    uint8_t epi;        // 0 = none (partial sum), 1 = scale/shift/ReLU -> bf16 operand, 2 = scale/shift/ReLU -> max-pool
 };
 
 struct TcArgs {
@@ -46,10 +56,14 @@ struct TcArgs {
     const float* new_xyz;
     const int64_t* idx;
     int N, S, K, D, rows;
-    TcLayer L[3];
-    uint32_t off_a, off_b, off_ss;  // activation ping-pong buffers, scale/shift staging
-    uint32_t tmem_cols;
-    unsigned int* out_bits;  // [B, Cout, S]
+    const unsigned char* blob;  // packed weights, then fp32 scale[total_ch], shift[total_ch]
+    uint32_t ss_blob_off;
+    int total_ch, kp0, cout;    // cout = channels of the pooled output row
+    int nsteps;
+    TcStep st[kTcMaxSteps];
+    uint32_t off_ring, stage_bytes, nstages, off_ss, off_pool, tmem_cols;
+    float* out;                 // [B*S, cout] point-major
+    int pool_atomic;            // 0: every group lies inside one tile (plain stores); 1: atomicMax merge
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -82,44 +96,63 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // warps 0-3 only
 
-// ---- weight pre-pack: fp32 [Cout, Cin] -> bf16 [kp/8][Cout][8], zero padded along K ------------
-__global__ void tc_pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int kp,
-                                       __nv_bfloat16* __restrict__ out) {
-    const int total = kp * cout;
+// ---- weight pre-pack: fp32 W[n0 + n, k0 + k] (row-major [Cout, Cin]) -> bf16 [kp/8][nlen][8], zero padded in K ----
+// feat_first >= 0 (layer 0): the kernel's operand holds the D = feat_first feature channels FIRST and the three
+// relative coordinates after them (16-byte aligned feature groups for the gather), i.e. operand row k is the
+// reference's input channel 3 + k for k < D and k - D for D <= k < D + 3 (models/pointnet2_encoder.py:99 order).
+__global__ void tc_pack_block_kernel(const float* __restrict__ w, int cin, int k0, int klen, int kp, int n0, int nlen,
+                                     int feat_first, __nv_bfloat16* __restrict__ out) {
+    const int total = kp * nlen;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int kc = e / (cout * 8);        // K chunk
-        const int rem = e % (cout * 8);
+        const int kc = e / (nlen * 8);
+        const int rem = e % (nlen * 8);
         const int n = rem / 8, ke = rem % 8;
         const int k = kc * 8 + ke;
-        out[e] = __float2bfloat16_rn(k < cin ? w[(size_t)n * cin + k] : 0.f);
+        int src = k0 + k;
+        if (feat_first >= 0) src = k < feat_first ? 3 + k : k - feat_first;
+        out[e] = __float2bfloat16_rn(k < klen ? w[(size_t)(n0 + n) * cin + src] : 0.f);
+    }
+}
+__global__ void tc_pack_ss_kernel(const float* __restrict__ scale, const float* __restrict__ shift, int n, int at,
+                                  int total_ch, float* __restrict__ out) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        out[at + c] = scale[c];
+        out[total_ch + at + c] = shift[c];
     }
 }
 
 __global__ void __launch_bounds__(kTcThreads)
-sa_mlp_tc_kernel(const TcArgs a) {
+sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t wbar[3];
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
+    __shared__ __align__(8) uint64_t mma_bar;  // accumulator of an epilogue-bearing step is complete
+    __shared__ __align__(8) uint64_t a_bar;    // an epilogue (or the gather) has finished: operand written, TMEM read
     __shared__ uint32_t tmem_base_sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = blockIdx.x * kTcM;
 
     if (tid == 0) {
-        for (int l = 0; l < 3; ++l) mbar_init(&wbar[l], 1);
+        for (int s = 0; s < kTcMaxStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
         mbar_init(&mma_bar, 1);
+        mbar_init(&a_bar, kTcEpiThreads);
         fence_mbar_init();
     }
-    if (warp == 0) {
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
                      "r"(a.tmem_cols)
                      : "memory");
@@ -130,210 +163,372 @@ sa_mlp_tc_kernel(const TcArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
 
-    // ---- weights: one TMA bulk copy per layer, all issued up front ----
-    if (tid == 0) {
-        for (int l = 0; l < 3; ++l) {
-            const uint32_t bytes = (uint32_t)a.L[l].kp * a.L[l].n * 2u;
-            mbar_arrive_expect_tx(&wbar[l], bytes);
-            tma_load_1d(smem + a.L[l].smem_off, a.L[l].w, bytes, &wbar[l]);
-        }
-    }
-    // ---- scale / shift of the three layers -> shared memory ----
-    float* ss = reinterpret_cast<float*>(smem + a.off_ss);  // [3][2][kTcMaxN]
-    for (int l = 0; l < 3; ++l)
-        for (int c = tid; c < a.L[l].n; c += kTcThreads) {
-            ss[(l * 2 + 0) * kTcMaxN + c] = a.L[l].scale[c];
-            ss[(l * 2 + 1) * kTcMaxN + c] = a.L[l].shift[c];
-        }
-
-    // ---- layer-0 operand: warp-cooperative gather, fp32 -> bf16, canonical [kp/8][128][8] layout ----
-    {
-        __nv_bfloat16* A0 = reinterpret_cast<__nv_bfloat16*>(smem + a.off_a);
-        const int kp0 = a.L[0].kp;
-        const int cin = 3 + a.D;
-        const int my_row = row0 + tid;
-        int my_j = 0, my_bs = 0;
-        if (my_row < a.rows) {
-            my_bs = my_row / a.K;
-            if (a.idx) {
-                const int64_t jj = a.idx[my_row];
-                my_j = jj < 0 ? 0 : (jj >= a.N ? a.N - 1 : (int)jj);
-            } else {
-                my_j = my_row % a.K;  // group_all: row k of cloud b is point k
+    if (warp == 4) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int s = 0; s < a.nsteps; ++s) {
+                const TcStep& st = a.st[s];
+                const unsigned char* src = a.blob + st.w_off;
+                for (int k0 = 0; k0 < st.kp; k0 += kTcChunkK, ++it) {
+                    const uint32_t stage = it % a.nstages;
+                    if (it >= a.nstages) mbar_wait(&empty_bar[stage], ((it / a.nstages) - 1u) & 1u);
+                    const int ck = st.kp - k0 < kTcChunkK ? st.kp - k0 : kTcChunkK;
+                    const uint32_t bytes = (uint32_t)ck * st.n * 2u;
+                    mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                    tma_load_1d(smem + a.off_ring + stage * a.stage_bytes, src + (size_t)k0 * st.n * 2u, bytes,
+                                &full_bar[stage]);
+                }
             }
         }
-        for (int r = 0; r < 32; ++r) {
-            const int m = warp * 32 + r;
-            const int row = row0 + m;
-            const int j = __shfl_sync(0xffffffffu, my_j, r);
-            const int bs = __shfl_sync(0xffffffffu, my_bs, r);
+    } else if (warp == 5) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, seen = 0, need = 1;  // events on a_bar: the gather, then one per epilogue
+            for (int s = 0; s < a.nsteps; ++s) {
+                const TcStep& st = a.st[s];
+                while (seen < need) {
+                    mbar_wait(&a_bar, seen & 1u);
+                    ++seen;
+                }
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_bf16(kTcM, st.n);
+                const uint32_t a_addr = smem_u32(smem + st.a_off);
+                const uint32_t lbo_a = kTcM * 16, lbo_w = (uint32_t)st.n * 16;
+                const uint32_t d_addr = tmem_base + st.tmem_col;
+                for (int k0 = 0; k0 < st.kp; k0 += kTcChunkK, ++it) {
+                    const uint32_t stage = it % a.nstages;
+                    mbar_wait(&full_bar[stage], (it / a.nstages) & 1u);
+                    tc_fence_after();
+                    const uint32_t w_addr = smem_u32(smem + a.off_ring + stage * a.stage_bytes);
+                    const int ck = st.kp - k0 < kTcChunkK ? st.kp - k0 : kTcChunkK;
+                    for (int kk = 0; kk < ck / 16; ++kk) {
+                        const int q = k0 / 16 + kk;  // K16 step inside the A operand
+                        const uint64_t ad = umma_smem_desc(a_addr + (uint32_t)q * 2u * lbo_a, lbo_a, 128);
+                        const uint64_t bd = umma_smem_desc(w_addr + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
+                        umma_bf16(d_addr, ad, bd, idesc, st.acc || q > 0);
+                    }
+                    umma_commit(&empty_bar[stage]);  // the stage is free once these MMAs have read it
+                }
+                if (st.epi) {
+                    umma_commit(&mma_bar);
+                    ++need;
+                }
+            }
+        }
+    } else {
+        // ================= gather + epilogues (128 threads, thread = row = TMEM lane) =================
+        float* ss = reinterpret_cast<float*>(smem + a.off_ss);  // scale[total_ch], shift[total_ch]
+        {
+            const float* src = reinterpret_cast<const float*>(a.blob + a.ss_blob_off);
+            for (int c = tid; c < 2 * a.total_ch; c += kTcEpiThreads) ss[c] = src[c];
+        }
+        {
+            // Layer-0 operand, one thread per row: operand row k = feature channel k (k < D), then the three
+            // relative coordinates, then zero padding up to kp0.  Features are read with 16 independent 128-bit
+            // loads in flight per thread and stored as 16-byte (8 x bf16) core-matrix rows: thread m writes
+            // [(k / 8) * 128 + m], so a warp's stores are contiguous (no bank conflicts).
+            unsigned char* A0b = smem + a.st[0].a_off;
+            __nv_bfloat16* A0 = reinterpret_cast<__nv_bfloat16*>(A0b);
+            const int D = a.D, kp0 = a.kp0;
+            const int row = row0 + tid;
+            const bool valid = row < a.rows;
+            int j = 0, bs = 0;
+            if (valid) {
+                bs = row / a.K;
+                if (a.idx) {
+                    const int64_t jj = a.idx[row];
+                    j = jj < 0 ? 0 : (jj >= a.N ? a.N - 1 : (int)jj);
+                } else {
+                    j = row % a.K;  // group_all: row k of cloud b is point k
+                }
+            }
             const int b = bs / a.S;
-            const bool valid = row < a.rows;
-            const float* prow = a.xyz + ((size_t)b * a.N + j) * 3;
-            const float* crow = a.new_xyz ? a.new_xyz + (size_t)bs * 3 : nullptr;
-            const float* frow = a.feats ? a.feats + ((size_t)b * a.N + j) * a.D : nullptr;
-            for (int c = lane; c < kp0; c += 32) {
+            float rel[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+                const float* p = a.xyz + ((size_t)b * a.N + j) * 3;
+                rel[0] = p[0]; rel[1] = p[1]; rel[2] = p[2];
+                if (a.new_xyz) {
+                    const float* c = a.new_xyz + (size_t)bs * 3;
+                    rel[0] = __fsub_rn(rel[0], c[0]); rel[1] = __fsub_rn(rel[1], c[1]); rel[2] = __fsub_rn(rel[2], c[2]);
+                }
+            }
+            const float* frow = D > 0 ? a.feats + ((size_t)b * a.N + j) * D : nullptr;
+            const bool vec = D > 0 && (D % 8) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
+            int kdone = 0;
+            if (vec) {
+                const int G = D / 8;
+                for (int g0 = 0; g0 < G; g0 += 8) {
+                    float4 v[16];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid && g0 + u < G) {
+                            v[2 * u] = __ldg(reinterpret_cast<const float4*>(frow + (g0 + u) * 8));
+                            v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(frow + (g0 + u) * 8 + 4));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (g0 + u < G) {
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[2 * u].x, v[2 * u].y);
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2 * u].z, v[2 * u].w);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * u + 1].x, v[2 * u + 1].y);
+                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[2 * u + 1].z, v[2 * u + 1].w);
+                            *reinterpret_cast<uint4*>(A0b + ((size_t)(g0 + u) * kTcM + tid) * 16) =
+                                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                           *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+                        }
+                    }
+                }
+                kdone = D;
+            }
+            for (int k = kdone; k < kp0; ++k) {  // feature tail (unaligned D), relative coordinates, zero padding
                 float v = 0.f;
-                if (valid && c < cin) {
-                    if (c < 3) {
-                        v = prow[c];
-                        if (crow) v = __fsub_rn(v, crow[c]);
-                    } else {
-                        v = __ldg(frow + (c - 3));
-                    }
-                }
-                A0[((size_t)(c >> 3) * kTcM + m) * 8 + (c & 7)] = __float2bfloat16_rn(v);
+                if (k < D) v = valid ? __ldg(frow + k) : 0.f;
+                else if (k - D < 3) v = (k - D) == 0 ? rel[0] : ((k - D) == 1 ? rel[1] : rel[2]);
+                A0[((size_t)(k >> 3) * kTcM + tid) * 8 + (k & 7)] = __float2bfloat16_rn(v);
             }
         }
-    }
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        epi_bar_sync();       // the scale/shift tables are complete for every epilogue thread
+        mbar_arrive(&a_bar);  // event 0: the layer-0 operand is in place
 
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-        const TcLayer& L = a.L[l];
-        const uint32_t in_off = (l == 1) ? a.off_b : a.off_a;   // L0: A -> B, L1: B -> A, L2: A -> pooled
-        const uint32_t out_off = (l == 0) ? a.off_b : a.off_a;
-        if (tid == 0) {
-            mbar_wait(&wbar[l], 0);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + in_off);
-            const uint32_t w_addr = smem_u32(smem + L.smem_off);
-            const uint32_t lbo_a = kTcM * 16, lbo_w = (uint32_t)L.n * 16;
-            const uint32_t idesc = umma_idesc_bf16(kTcM, L.n);
-            for (int kk = 0; kk < L.kp / 16; ++kk) {
-                const uint64_t ad = umma_smem_desc(a_addr + (uint32_t)kk * 2u * lbo_a, lbo_a, 128);
-                const uint64_t bd = umma_smem_desc(w_addr + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
-                umma_bf16(tmem_base, ad, bd, idesc, kk > 0);
-            }
-            umma_commit(&mma_bar);  // arrives when every MMA above has completed
-        }
-        mbar_wait(&mma_bar, (uint32_t)(l & 1));
-        tc_fence_after();
-
-        const float* sc = ss + (l * 2 + 0) * kTcMaxN;
-        const float* sh = ss + (l * 2 + 1) * kTcMaxN;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
         const int m = tid;  // this thread's row = its TMEM lane
-        if (l < 2) {
-            unsigned char* outp = smem + out_off;
-            for (int c0 = 0; c0 < L.n; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t)c0, r);
-                uint32_t packed[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float y0 = __fmaf_rn(__uint_as_float(r[2 * i]), sc[c0 + 2 * i], sh[c0 + 2 * i]);
-                    float y1 = __fmaf_rn(__uint_as_float(r[2 * i + 1]), sc[c0 + 2 * i + 1], sh[c0 + 2 * i + 1]);
-                    y0 = y0 > 0.f ? y0 : 0.f;
-                    y1 = y1 > 0.f ? y1 : 0.f;
-                    __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                    packed[i] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                // channels c0..c0+7 and c0+8..c0+15 are two K chunks of the next operand
-                uint4* d0 = reinterpret_cast<uint4*>(outp + ((size_t)(c0 >> 3) * kTcM + m) * 16);
-                uint4* d1 = reinterpret_cast<uint4*>(outp + ((size_t)((c0 >> 3) + 1) * kTcM + m) * 16);
-                *d0 = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *d1 = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();
+        uint32_t mma_phase = 0;
+        for (int s = 0; s < a.nsteps; ++s) {
+            const TcStep& st = a.st[s];
+            if (!st.epi) continue;
+            mbar_wait(&mma_bar, mma_phase & 1u);
+            ++mma_phase;
             tc_fence_after();
-        } else {
-            // ---- last layer: max over each group's K rows, merged with atomicMax on the fp32 bits ----
-            const int row = row0 + m;
-            const bool valid = row < a.rows;
-            const bool warp_uniform_group = (a.K % 32) == 0;  // the warp's 32 rows belong to one group
-            const int wrow = row0 + warp * 32;
-            const int g = (warp_uniform_group ? wrow : (valid ? row : 0)) / a.K;
-            const int b = g / a.S, s = g % a.S;
-            unsigned int* obase = a.out_bits + ((size_t)b * L.n) * a.S + s;
-            for (int c0 = 0; c0 < L.n; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t)c0, r);
-                unsigned int mine = 0;
+            const float* sc = ss + st.ss_idx;
+            const float* sh = ss + a.total_ch + st.ss_idx;
+            const uint32_t taddr = taddr_lane + st.tmem_col;
+            if (st.epi == 1) {
+                unsigned char* outp = smem + st.out_off;
+                for (int c0 = 0; c0 < st.n; c0 += 32) {
+                    uint32_t r[2][16];
+                    tmem_ld16_issue(taddr + (uint32_t)c0, r[0]);
+                    const bool two = c0 + 16 < st.n;
+                    if (two) tmem_ld16_issue(taddr + (uint32_t)c0 + 16u, r[1]);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float y = __fmaf_rn(__uint_as_float(r[i]), sc[c0 + i], sh[c0 + i]);
-                    y = (valid && y > 0.f) ? y : 0.f;
-                    if (warp_uniform_group) {
-                        const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
-                        if (lane == i) mine = mx;
-                    } else if (valid) {
-                        atomicMax(obase + (size_t)(c0 + i) * a.S, __float_as_uint(y));
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !two) break;
+                        const int cb = c0 + 16 * h;
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float y0 = __fmaf_rn(__uint_as_float(r[h][2 * i]), sc[cb + 2 * i], sh[cb + 2 * i]);
+                            float y1 = __fmaf_rn(__uint_as_float(r[h][2 * i + 1]), sc[cb + 2 * i + 1], sh[cb + 2 * i + 1]);
+                            y0 = y0 > 0.f ? y0 : 0.f;
+                            y1 = y1 > 0.f ? y1 : 0.f;
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(y0, y1);
+                            packed[i] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                        // channels cb..cb+7 and cb+8..cb+15 are two K chunks of the next operand
+                        uint4* d0 = reinterpret_cast<uint4*>(outp + ((size_t)(cb >> 3) * kTcM + m) * 16);
+                        uint4* d1 = reinterpret_cast<uint4*>(outp + ((size_t)((cb >> 3) + 1) * kTcM + m) * 16);
+                        *d0 = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        *d1 = make_uint4(packed[4], packed[5], packed[6], packed[7]);
                     }
                 }
-                if (warp_uniform_group && lane < 16 && wrow < a.rows)
-                    atomicMax(obase + (size_t)(c0 + lane) * a.S, mine);
+                fence_proxy_async();
+            } else {
+                // ---- max over each group's K rows ----
+                const int row = row0 + m;
+                const bool valid = row < a.rows;
+                if (!a.pool_atomic) {
+                    // K in {32, 64, 128}: the warp's 32 rows belong to one group and every group lies in this tile
+                    float* pool = reinterpret_cast<float*>(smem + a.off_pool);  // [4 warps][n]
+                    for (int c0 = 0; c0 < st.n; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16_issue(taddr + (uint32_t)c0, r);
+                        tmem_ld_wait();
+                        unsigned int mine = 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float y = __fmaf_rn(__uint_as_float(r[i]), sc[c0 + i], sh[c0 + i]);
+                            y = (valid && y > 0.f) ? y : 0.f;  // post-ReLU values are >= +0: bits order like unsigned
+                            const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
+                            if (lane == i) mine = mx;
+                        }
+                        if (lane < 16) pool[warp * st.n + c0 + lane] = __uint_as_float(mine);
+                    }
+                    epi_bar_sync();
+                    const int wpg = a.K / 32;       // warps per group
+                    const int groups = kTcM / a.K;  // groups per tile
+                    const int g0 = row0 / a.K;      // first group (= b * S + s) of the tile
+                    for (int e = tid; e < groups * st.n; e += kTcEpiThreads) {
+                        const int g = e / st.n, c = e % st.n;
+                        if ((size_t)(g0 + g) * a.K >= (size_t)a.rows) continue;
+                        float v = pool[(g * wpg) * st.n + c];
+                        for (int w = 1; w < wpg; ++w) v = fmaxf(v, pool[(g * wpg + w) * st.n + c]);
+                        a.out[(size_t)(g0 + g) * a.cout + st.out_c0 + c] = v;
+                    }
+                    epi_bar_sync();  // pool is reused by the next pooled step
+                } else {
+                    const bool warp_uniform_group = (a.K % 32) == 0;
+                    const int wrow = row0 + warp * 32;
+                    const int g = (warp_uniform_group ? wrow : (valid ? row : 0)) / a.K;
+                    unsigned int* obase = reinterpret_cast<unsigned int*>(a.out) + (size_t)g * a.cout + st.out_c0;
+                    for (int c0 = 0; c0 < st.n; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16_issue(taddr + (uint32_t)c0, r);
+                        tmem_ld_wait();
+                        unsigned int mine = 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float y = __fmaf_rn(__uint_as_float(r[i]), sc[c0 + i], sh[c0 + i]);
+                            y = (valid && y > 0.f) ? y : 0.f;
+                            if (warp_uniform_group) {
+                                const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
+                                if (lane == i) mine = mx;
+                            } else if (valid) {
+                                atomicMax(obase + c0 + i, __float_as_uint(y));
+                            }
+                        }
+                        if (warp_uniform_group && lane < 16 && wrow < a.rows) atomicMax(obase + c0 + lane, mine);
+                    }
+                }
             }
+            tc_fence_before();
+            mbar_arrive(&a_bar);  // operand written / accumulator drained: later steps may proceed
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols)
                      : "memory");
     }
 }
 
+// ---- host side: the step table, the shared-memory layout and the packed-blob layout ----------------
+struct TcBlock {
+    int layer, k0, klen, kp, n0, nlen;
+    uint32_t w_off;
+};
 struct TcPlan {
-    int kp[3], n[3];
-    uint32_t off_w[3], off_a, off_b, off_ss, smem_bytes, tmem_cols;
-    size_t ws_w[3], ws_total;
     bool ok;
+    int nsteps, nblocks, kp0, total_ch;
+    int n[3];
+    TcStep st[kTcMaxSteps];
+    TcBlock blk[kTcMaxBlocks];
+    uint32_t off_ring, stage_bytes, nstages, off_ss, off_pool, smem_bytes, tmem_cols, ss_blob_off;
+    size_t blob_bytes;
 };
 
-static TcPlan tc_plan(int D, const pcst_mlp3_t* mlp) {
+static TcPlan tc_plan(int D, const int* cout) {
     TcPlan p = {};
-    int cin = 3 + D;
-    uint32_t off = 0;
-    size_t ws = 0;
-    int maxn = 0;
-    p.ok = true;
+    p.ok = false;
+    const int n0 = cout[0], n1 = cout[1], n2 = cout[2];
     for (int l = 0; l < 3; ++l) {
-        p.kp[l] = (int)align_up((size_t)cin, 16);
-        p.n[l] = mlp->cout[l];
-        if (p.n[l] > kTcMaxN || (p.n[l] % 32) != 0) p.ok = false;
-        p.off_w[l] = off;
-        off += (uint32_t)align_up((size_t)p.kp[l] * p.n[l] * 2, 128);
-        p.ws_w[l] = ws;
-        ws += align_up((size_t)p.kp[l] * p.n[l] * 2, 256);
-        if (p.n[l] > maxn) maxn = p.n[l];
-        cin = p.n[l];
+        p.n[l] = cout[l];
+        if (cout[l] <= 0 || (cout[l] % 32) != 0 || cout[l] > 2 * kTcMaxN) return p;
     }
-    const int a_k = p.kp[0] > p.n[1] ? p.kp[0] : p.n[1];  // buffer A: layer-0 input, later layer-1 output
-    p.off_a = off;
-    off += (uint32_t)kTcM * a_k * 2;
-    p.off_b = off;
-    off += (uint32_t)kTcM * p.n[0] * 2;
-    p.off_ss = off;
-    off += 3 * 2 * kTcMaxN * sizeof(float);
-    p.smem_bytes = off;
-    p.tmem_cols = maxn <= 32 ? 32 : maxn <= 64 ? 64 : maxn <= 128 ? 128 : 256;
-    p.ws_total = ws;
-    if (p.smem_bytes > 220 * 1024) p.ok = false;
+    if (n0 > kTcMaxN) return p;
+    const int h1 = n1 > kTcMaxN ? 2 : 1, h2 = n2 > kTcMaxN ? 2 : 1;  // N halves of layers 1 and 2
+    const int n1h = n1 / h1, n2h = n2 / h2;
+    p.kp0 = (int)align_up((size_t)(3 + D), 16);
+    p.total_ch = n0 + n1 + n2;
+
+    // weight blocks in the blob
+    uint32_t woff = 0;
+    auto add_block = [&](int layer, int k0, int klen, int kp, int nb0, int nlen) -> uint32_t {
+        TcBlock& b = p.blk[p.nblocks++];
+        b.layer = layer; b.k0 = k0; b.klen = klen; b.kp = kp; b.n0 = nb0; b.nlen = nlen; b.w_off = woff;
+        woff += (uint32_t)align_up((size_t)kp * nlen * 2, 128);
+        return b.w_off;
+    };
+    const uint32_t w0 = add_block(0, 0, 3 + D, p.kp0, 0, n0);
+    uint32_t w1[2] = {0, 0}, w2[2][2] = {{0, 0}, {0, 0}};
+    for (int kh = 0; kh < h1; ++kh) w1[kh] = add_block(1, 0, n0, n0, kh * n1h, n1h);
+    for (int fh = 0; fh < h2; ++fh)
+        for (int kh = 0; kh < h1; ++kh) w2[kh][fh] = add_block(2, kh * n1h, n1h, n1h, fh * n2h, n2h);
+    p.ss_blob_off = woff;
+    p.blob_bytes = (size_t)woff + (size_t)2 * p.total_ch * sizeof(float);
+
+    // shared memory
+    const int max_n = n0 > n1h ? (n0 > n2h ? n0 : n2h) : (n1h > n2h ? n1h : n2h);
+    p.stage_bytes = (uint32_t)max_n * kTcChunkK * 2;
+    const uint32_t size_x = (uint32_t)kTcM * (p.kp0 > n1h ? p.kp0 : n1h) * 2;  // layer-0 input, later a layer-1 half
+    const uint32_t size_h = (uint32_t)kTcM * n0 * 2;                             // layer-0 output
+    const uint32_t size_ss = (uint32_t)align_up((size_t)2 * p.total_ch * sizeof(float), 128);
+    const uint32_t size_pool = (uint32_t)align_up((size_t)4 * n2h * sizeof(float), 128);
+    const uint32_t fixed = size_x + size_h + size_ss + size_pool;
+    const uint32_t limit = 225 * 1024;
+    int total_chunks = (p.kp0 + kTcChunkK - 1) / kTcChunkK;
+    total_chunks += h2 * h1 * ((n0 + kTcChunkK - 1) / kTcChunkK + (n1h + kTcChunkK - 1) / kTcChunkK);
+    p.nstages = kTcMaxStages;
+    while (p.nstages > 2 && (fixed + p.nstages * p.stage_bytes > limit || (int)p.nstages > total_chunks)) --p.nstages;
+    if (fixed + p.nstages * p.stage_bytes > limit) return p;
+    p.off_ring = 0;
+    const uint32_t off_x = p.nstages * p.stage_bytes;
+    const uint32_t off_h = off_x + size_x;
+    p.off_ss = off_h + size_h;
+    p.off_pool = p.off_ss + size_ss;
+    p.smem_bytes = p.off_pool + size_pool;
+
+    // steps
+    const bool split = h1 * h2 > 1;
+    auto add_step = [&](uint32_t a_off, uint32_t out_off, uint32_t w_off, int kp, int n, int col, int out_c0, int ss_idx,
+                        int acc, int epi) {
+        TcStep& s = p.st[p.nsteps++];
+        s.a_off = a_off; s.out_off = out_off; s.w_off = w_off; s.kp = (uint16_t)kp; s.n = (uint16_t)n;
+        s.tmem_col = (uint16_t)col; s.out_c0 = (uint16_t)out_c0; s.ss_idx = (uint16_t)ss_idx;
+        s.acc = (uint8_t)acc; s.epi = (uint8_t)epi;
+    };
+    add_step(off_x, off_h, w0, p.kp0, n0, 0, 0, 0, 0, 1);
+    for (int fh = 0; fh < h2; ++fh)
+        for (int kh = 0; kh < h1; ++kh) {
+            add_step(off_h, off_x, w1[kh], n0, n1h, split ? kTcMaxN : 0, 0, n0 + kh * n1h, 0, 1);
+            add_step(off_x, 0, w2[kh][fh], n1h, n2h, 0, fh * n2h, n0 + n1 + fh * n2h, kh > 0, kh == h1 - 1 ? 2 : 0);
+        }
+    const int cols = split ? 2 * kTcMaxN : max_n;
+    p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    p.ok = true;
     return p;
 }
 
-bool sa_mlp_max_tc_supported(int D, const pcst_mlp3_t* mlp) { return tc_plan(D, mlp).ok; }
+bool sa_mlp_tc_supported(int D, const int* cout) { return tc_plan(D, cout).ok; }
+size_t sa_mlp_tc_blob_bytes(int D, const int* cout) { return tc_plan(D, cout).blob_bytes; }
 
-size_t sa_mlp_max_tc_workspace(int B, int N, int S, int K, int D, const pcst_mlp3_t* mlp) {
-    (void)B; (void)N; (void)S; (void)K;
-    return tc_plan(D, mlp).ws_total + 256;
-}
-
-int sa_mlp_max_tc(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
-                  int K, int D, const pcst_mlp3_t* mlp, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    const TcPlan p = tc_plan(D, mlp);
+int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, void* blob, cudaStream_t stream) {
+    const TcPlan p = tc_plan(D, mlp->cout);
     if (!p.ok) {
-        set_error("sa_mlp_max (tensor-core path): needs Cout <= 256 (multiple of 32) and <= 220 KiB of shared memory");
+        set_error("sa_mlp pack (tensor-core path): unsupported layer widths");
         return PCST_ERR_UNSUPPORTED;
     }
-    if (ws_bytes < p.ws_total) return PCST_ERR_WORKSPACE;
+    const int cin[3] = {3 + D, p.n[0], p.n[1]};
+    for (int i = 0; i < p.nblocks; ++i) {
+        const TcBlock& b = p.blk[i];
+        const int total = b.kp * b.nlen;
+        tc_pack_block_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
+            mlp->w[b.layer], cin[b.layer], b.k0, b.klen, b.kp, b.n0, b.nlen, b.layer == 0 ? D : -1,
+            reinterpret_cast<__nv_bfloat16*>((char*)blob + b.w_off));
+        PCST_CUDA(cudaGetLastError());
+    }
+    float* ss = reinterpret_cast<float*>((char*)blob + p.ss_blob_off);
+    int at = 0;
+    for (int l = 0; l < 3; ++l) {
+        tc_pack_ss_kernel<<<(p.n[l] + 255) / 256, 256, 0, stream>>>(mlp->scale[l], mlp->shift[l], p.n[l], at, p.total_ch, ss);
+        PCST_CUDA(cudaGetLastError());
+        at += p.n[l];
+    }
+    return PCST_OK;
+}
+
+int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
+                  int K, int D, const int* cout, const void* blob, float* out, cudaStream_t stream) {
+    const TcPlan p = tc_plan(D, cout);
+    if (!p.ok) {
+        set_error("sa_mlp_max (tensor-core path): unsupported layer widths");
+        return PCST_ERR_UNSUPPORTED;
+    }
     const size_t rows_sz = (size_t)B * S * K;
     if (rows_sz >= (1u << 30)) {
         set_error("sa_mlp_max: B*S*K too large");
@@ -342,19 +537,16 @@ int sa_mlp_max_tc(const float* xyz, const float* feats, const float* new_xyz, co
     TcArgs a = {};
     a.xyz = xyz; a.feats = feats; a.new_xyz = new_xyz; a.idx = idx;
     a.N = N; a.S = S; a.K = K; a.D = D; a.rows = (int)rows_sz;
-    int cin = 3 + D;
-    for (int l = 0; l < 3; ++l) {
-        __nv_bfloat16* wp = (__nv_bfloat16*)((char*)ws + p.ws_w[l]);
-        const int total = p.kp[l] * p.n[l];
-        tc_pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(mlp->w[l], p.n[l], cin, p.kp[l], wp);
-        PCST_CUDA(cudaGetLastError());
-        a.L[l].w = wp; a.L[l].scale = mlp->scale[l]; a.L[l].shift = mlp->shift[l];
-        a.L[l].kp = p.kp[l]; a.L[l].n = p.n[l]; a.L[l].smem_off = p.off_w[l];
-        cin = p.n[l];
-    }
-    a.off_a = p.off_a; a.off_b = p.off_b; a.off_ss = p.off_ss; a.tmem_cols = p.tmem_cols;
-    a.out_bits = (unsigned int*)out;
-    PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * p.n[2] * S * sizeof(float), stream));
+    a.blob = (const unsigned char*)blob;
+    a.ss_blob_off = p.ss_blob_off;
+    a.total_ch = p.total_ch; a.kp0 = p.kp0; a.cout = cout[2];
+    a.nsteps = p.nsteps;
+    for (int s = 0; s < p.nsteps; ++s) a.st[s] = p.st[s];
+    a.off_ring = p.off_ring; a.stage_bytes = p.stage_bytes; a.nstages = p.nstages;
+    a.off_ss = p.off_ss; a.off_pool = p.off_pool; a.tmem_cols = p.tmem_cols;
+    a.out = out;
+    a.pool_atomic = !(K == 32 || K == 64 || K == 128);
+    if (a.pool_atomic) PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * cout[2] * sizeof(float), stream));
     PCST_CUDA(cudaFuncSetAttribute(sa_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     const int grid = (a.rows + kTcM - 1) / kTcM;
     sa_mlp_tc_kernel<<<grid, kTcThreads, p.smem_bytes, stream>>>(a);

@@ -14,6 +14,9 @@ import torch.nn.functional as F
 from .. import ops
 
 
+_SIDE_STREAMS = {}  # device -> side stream of the overlapped inference schedule (PointNet2Encoder._forward_overlapped)
+
+
 def _cuda_only(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor; pointcloud_style_transfer_b200 has no CPU fallback")
@@ -84,6 +87,7 @@ class SetAbstraction(nn.Module):
         self.group_all = group_all
         self._fold_key = None
         self._fold = None
+        self._packed = {}
 
     # -- eval-mode folding of conv bias + BatchNorm into per-channel (scale, shift) ------------------
     def _folded(self):
@@ -111,7 +115,18 @@ class SetAbstraction(nn.Module):
                     shs.append(shift.float().contiguous())
                     cin_pad = cout_pad
             self._fold, self._fold_key = (ws, scs, shs), key
+            self._packed = {}
         return self._fold
+
+    def _packed_params(self):
+        """The folded parameters in the layout the kernels read, packed once per parameter version and
+        precision (bf16 UMMA operand blocks for the tensor-core path) -> (uint8 blob, padded Couts)."""
+        ws, scs, shs = self._folded()
+        prec = int(self.mlp_precision)
+        if prec not in self._packed:
+            D = ws[0].shape[1] - 3
+            self._packed[prec] = (ops.sa_mlp_pack(ws, scs, shs, D, prec), [int(w.shape[0]) for w in ws])
+        return self._packed[prec]
 
     def _fused_ok(self, *tensors) -> bool:
         if self.training or len(self.mlp_convs) != 3:
@@ -133,9 +148,9 @@ class SetAbstraction(nn.Module):
         if self.group_all:
             new_xyz = torch.zeros(B, 1, 3, device=xyz.device)  # :82
             if fused:
-                ws, scs, shs = self._folded()
-                new_points = ops.sa_mlp_max(xyz, points, None, None, ws, scs, shs, self.mlp_precision)[:, :cout]
-                return new_xyz, new_points.squeeze(-1)
+                packed, couts = self._packed_params()
+                new_points = ops.sa_mlp_max(xyz, points, None, None, packed, couts, self.mlp_precision)  # [B,1,C]
+                return new_xyz, new_points[:, 0, :cout]
             if points is not None:
                 grouped_points = torch.cat([xyz.view(B, 1, N, 3), points.view(B, 1, N, -1)], dim=-1)
             else:
@@ -143,31 +158,39 @@ class SetAbstraction(nn.Module):
             new_points = self.apply_mlp(grouped_points)
             return new_xyz, new_points.squeeze(-1)
 
-        if start is None:
-            farthest = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)  # :36, CPU generator
-        else:
-            farthest = start
-        _, new_xyz = ops.fps(xyz, int(self.npoint), farthest)                  # :91-92 (indices + gather)
-        group_idx = query_ball_point(self.radius, self.nsample, xyz, new_xyz)  # :93
+        new_xyz, group_idx = self._sample_group(xyz, start)
         if fused:
-            ws, scs, shs = self._folded()
-            new_points = ops.sa_mlp_max(xyz, points, new_xyz, group_idx, ws, scs, shs, self.mlp_precision)[:, :cout]
-            return new_xyz, new_points
+            return new_xyz, self._mlp_fused(xyz, points, new_xyz, group_idx)
         new_points = ops.group(xyz, points, new_xyz, group_idx)                # :94-101
         new_points = self.apply_mlp(new_points)
         return new_xyz, new_points
+
+    def _sample_group(self, xyz: torch.Tensor, start: Optional[torch.Tensor] = None):
+        """FPS (+ centroid gather, :91-92) and ball query (:93) -> (new_xyz [B,S,3], group_idx [B,S,K])."""
+        B, N, _ = xyz.shape
+        if start is None:
+            start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)  # :36, CPU generator
+        _, new_xyz = ops.fps(xyz, int(self.npoint), start)
+        return new_xyz, query_ball_point(self.radius, self.nsample, xyz, new_xyz)
+
+    def _mlp_fused(self, xyz, points, new_xyz, group_idx) -> torch.Tensor:
+        """Grouping gather + folded MLP + max-pool in one op -> [B,C_out,S] (a channel-first VIEW of the
+        kernel's point-major output, so the caller's permute back, :128-129, is free)."""
+        packed, couts = self._packed_params()
+        out = ops.sa_mlp_max(xyz, points, new_xyz, group_idx, packed, couts, self.mlp_precision)  # [B,S,C]
+        return out[:, :, :self.mlp_convs[-1].out_channels].permute(0, 2, 1)
 
     def apply_mlp(self, points):
         """models/pointnet2_encoder.py:106-112.  points [B,S,K,C] -> [B,C_out,S]."""
         if self._fused_ok(points) and points.is_cuda:
             # a pre-grouped tensor: run it as B*S clouds of K points, one group each (group_all form)
             B, S, K, C = points.shape
-            ws, scs, shs = self._folded()
+            packed, couts = self._packed_params()
             flat = points.reshape(B * S, K, C)
             xyz = flat[..., :3].contiguous()
             feats = flat[..., 3:].contiguous() if C > 3 else None
-            out = ops.sa_mlp_max(xyz, feats, None, None, ws, scs, shs, self.mlp_precision)
-            return out[:, :self.mlp_convs[-1].out_channels, 0].reshape(B, S, -1).permute(0, 2, 1)
+            out = ops.sa_mlp_max(xyz, feats, None, None, packed, couts, self.mlp_precision)  # [B*S,1,C]
+            return out[:, 0, :self.mlp_convs[-1].out_channels].reshape(B, S, -1).permute(0, 2, 1)
         points = points.permute(0, 3, 1, 2)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             points = F.relu(bn(conv(points)))
@@ -186,6 +209,34 @@ class PointNet2Encoder(nn.Module):
                                   in_channel=256, mlp=[256, 512, feature_dim], group_all=True)
         self.set_mlp_precision(mlp_precision)
 
+    def _forward_overlapped(self, xyz: torch.Tensor, s1, s2) -> torch.Tensor:
+        """Inference schedule of the same three stages.  Stage 2's sampling and grouping (FPS over the 512
+        stage-1 centroids, then ball query) only need stage 1's CENTROIDS, not its features, so they run on a
+        side stream next to stage 1's ball query + MLP; the two streams join before stage 2's MLP.  Under
+        ``runtime.GraphedEncoder`` the fork / join is captured into the CUDA graph as parallel branches."""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        if s1 is None:  # the reference's two draws, in its order (:36 inside sa1, then inside sa2)
+            s1 = torch.randint(0, N, (B,), dtype=torch.long).to(dev)
+            s2 = torch.randint(0, self.sa1.npoint, (B,), dtype=torch.long).to(dev)
+        main = torch.cuda.current_stream(dev)
+        side = _SIDE_STREAMS.get(dev)
+        if side is None:
+            side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        _, l1_xyz = ops.fps(xyz, int(self.sa1.npoint), s1)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            l2_xyz, idx2 = self.sa2._sample_group(l1_xyz, s2)
+        idx1 = query_ball_point(self.sa1.radius, self.sa1.nsample, xyz, l1_xyz)
+        l1_points = self.sa1._mlp_fused(xyz, None, l1_xyz, idx1)                  # [B,128,512]
+        main.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (l2_xyz, idx2):  # allocated on the side stream, consumed on the main stream
+                t.record_stream(main)
+        l2_points = self.sa2._mlp_fused(l1_xyz, l1_points.permute(0, 2, 1), l2_xyz, idx2)   # [B,256,128]
+        _, global_feature = self.sa3(l2_xyz, l2_points.permute(0, 2, 1))
+        return global_feature.view(B, -1)
+
     def set_mlp_precision(self, precision: int) -> "PointNet2Encoder":
         """0 = fp32 CUDA cores (parity within rtol 1e-4), 1 = bf16 tcgen05 tensor cores (rtol 2e-2)."""
         for sa in (self.sa1, self.sa2, self.sa3):
@@ -198,6 +249,8 @@ class PointNet2Encoder(nn.Module):
         B, N, C = xyz.shape
         points = None
         s1, s2 = starts if starts is not None else (None, None)
+        if xyz.is_cuda and all(sa._fused_ok(xyz) for sa in (self.sa1, self.sa2, self.sa3)):
+            return self._forward_overlapped(xyz, s1, s2)
         l1_xyz, l1_points = self.sa1(xyz, points, s1)                           # [B,128,512]
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points.permute(0, 2, 1), s2)    # [B,256,128]
         _, global_feature = self.sa3(l2_xyz, l2_points.permute(0, 2, 1))        # [B,feature_dim]

@@ -52,7 +52,7 @@ def _workspace(nbytes: int, device) -> Tensor:
 # roofline's live kernel durations).  KERNELS_PER_CALL counts __global__ launches (memsets excluded).
 KERNELS_PER_CALL = {"pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
-                    "pcst_sa_mlp_max_f32": 3, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
+                    "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 7, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
                     "pcst_knn_interpolate_f32": 1}
 launch_count = 0
 _event_log = None  # None = off; else list of (name, start_event, end_event)
@@ -74,7 +74,7 @@ def stop_event_log():
     return out
 
 
-def _call(name: str, *args) -> None:
+def _call(name: str, *args, kernels: Optional[int] = None) -> None:
     global launch_count
     fn = getattr(_lib.load(), name)
     if _event_log is None:
@@ -85,7 +85,7 @@ def _call(name: str, *args) -> None:
         check(fn(*args))
         b.record()
         _event_log.append((name, a, b))
-    launch_count += KERNELS_PER_CALL[name]
+    launch_count += KERNELS_PER_CALL[name] if kernels is None else kernels
 
 
 # ------------------------------------------------------------------------------------------ FPS
@@ -128,7 +128,7 @@ def ball_query(xyz: Tensor, new_xyz: Tensor, radius_sq: float, nsample: int) -> 
     with torch.cuda.device(xyz.device):
         ws = _workspace(lib.pcst_ball_query_workspace_bytes(B, N, S), xyz.device)
         _call("pcst_ball_query_f32", _p(xyz), _p(new_xyz), B, N, S, ctypes.c_float(radius_sq), nsample, _p(out),
-                                      _p(ws), ws.numel(), _stream())
+              _p(ws), ws.numel(), _stream(), kernels=1 if N <= 2048 else 2)
     return out
 
 
@@ -256,50 +256,81 @@ group.register_autograd(_group_backward, setup_context=_group_setup)
 # ---------------------------------------------------------------------------- SA MLP + max-pool
 
 
+def _cout3(couts: List[int]):
+    if len(couts) != 3:
+        raise ValueError("sa_mlp: the kernels implement the reference's 3-layer shared MLP")
+    return (ctypes.c_int * 3)(*[int(c) for c in couts])
+
+
+@torch.library.custom_op("pcst::sa_mlp_pack", mutates_args=(), device_types="cuda")
+def sa_mlp_pack(weights: List[Tensor], scales: List[Tensor], shifts: List[Tensor], D: int, precision: int) -> Tensor:
+    """Pack the folded parameters of a 3-layer shared MLP once (bf16 UMMA operand blocks for the tensor-core
+    path, a plain fp32 blob otherwise) -> uint8 tensor, reused by every ``sa_mlp_max`` call."""
+    lib = _lib.load()
+    _need_cuda(*weights, *scales, *shifts)
+    if len(weights) != 3 or len(scales) != 3 or len(shifts) != 3:
+        raise ValueError("sa_mlp_pack: the kernels implement the reference's 3-layer shared MLP")
+    weights = [_f32c(w.reshape(w.shape[0], -1)) for w in weights]
+    scales = [_f32c(s) for s in scales]
+    shifts = [_f32c(s) for s in shifts]
+    m = Mlp3()
+    cin = 3 + D
+    for l in range(3):
+        if weights[l].shape[1] != cin:
+            raise ValueError(f"sa_mlp_pack: layer {l} expects Cin={weights[l].shape[1]}, got {cin}")
+        m.w[l], m.scale[l], m.shift[l] = weights[l].data_ptr(), scales[l].data_ptr(), shifts[l].data_ptr()
+        m.cout[l] = cin = weights[l].shape[0]
+    dev = weights[0].device
+    with torch.cuda.device(dev):
+        nb = lib.pcst_sa_mlp_packed_bytes(D, m.cout, precision)
+        if nb == 0:
+            raise ValueError("sa_mlp_pack: unsupported layer widths (Cout must be a multiple of 32, <= 1024)")
+        packed = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _call("pcst_sa_mlp_pack_f32", ctypes.byref(m), D, precision, _p(packed), nb, _stream())
+    return packed
+
+
+@sa_mlp_pack.register_fake
+def _(weights, scales, shifts, D, precision):
+    return weights[0].new_empty(1, dtype=torch.uint8)
+
+
 @torch.library.custom_op("pcst::sa_mlp_max", mutates_args=(), device_types="cuda")
 def sa_mlp_max(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], idx: Optional[Tensor],
-               weights: List[Tensor], scales: List[Tensor], shifts: List[Tensor], precision: int) -> Tensor:
-    """Fused grouping gather + 3 x relu(scale * (W x) + shift) + max over each group -> [B,Cout,S].
+               packed: Tensor, couts: List[int], precision: int) -> Tensor:
+    """Fused grouping gather + 3 x relu(scale * (W x) + shift) + max over each group -> [B,S,Cout] (POINT-major;
+    the reference's channel-first layout is ``.permute(0, 2, 1)``).
 
-    ``idx is None`` = group_all (one group holding the whole cloud, no centroid subtraction)."""
+    ``idx is None`` = group_all (one group holding the whole cloud, no centroid subtraction);
+    ``packed`` comes from ``sa_mlp_pack`` with the same ``couts`` / ``precision`` / D."""
     lib = _lib.load()
-    _need_cuda(xyz, feats, new_xyz, idx, *weights, *scales, *shifts)
-    if len(weights) != 3 or len(scales) != 3 or len(shifts) != 3:
-        raise ValueError("sa_mlp_max: the kernel implements the reference's 3-layer shared MLP")
+    _need_cuda(xyz, feats, new_xyz, idx, packed)
     xyz = _f32c(xyz)
     feats = None if feats is None else _f32c(feats)
     new_xyz = None if new_xyz is None else _f32c(new_xyz)
     idx = None if idx is None else _i64c(idx)
-    weights = [_f32c(w.reshape(w.shape[0], -1)) for w in weights]
-    scales = [_f32c(s) for s in scales]
-    shifts = [_f32c(s) for s in shifts]
     B, N, _ = xyz.shape
     D = 0 if feats is None else feats.shape[2]
     if idx is None:
         S, K = 1, N
     else:
         _, S, K = idx.shape
-    cin = 3 + D
-    m = Mlp3()
-    for l in range(3):
-        if weights[l].shape[1] != cin:
-            raise ValueError(f"sa_mlp_max: layer {l} expects Cin={weights[l].shape[1]}, got {cin}")
-        m.w[l], m.scale[l], m.shift[l] = weights[l].data_ptr(), scales[l].data_ptr(), shifts[l].data_ptr()
-        m.cout[l] = weights[l].shape[0]
-        cin = weights[l].shape[0]
-    out = torch.empty(B, cin, S, dtype=torch.float32, device=xyz.device)
+    c3 = _cout3(couts)
+    out = torch.empty(B, S, int(couts[2]), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
-        nb = lib.pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, ctypes.byref(m), precision)
+        if packed.numel() < lib.pcst_sa_mlp_packed_bytes(D, c3, precision):
+            raise ValueError("sa_mlp_max: `packed` does not match (D, couts, precision)")
+        nb = lib.pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, c3, precision)
         ws = _workspace(nb, xyz.device)
-        _call("pcst_sa_mlp_max_f32", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, ctypes.byref(m),
-                                      precision, _p(out), _p(ws), ws.numel(), _stream())
+        _call("pcst_sa_mlp_max_f32", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, c3, precision,
+              _p(packed), _p(out), _p(ws), ws.numel(), _stream(), kernels=1 if nb == 0 else 3)
     return out
 
 
 @sa_mlp_max.register_fake
-def _(xyz, feats, new_xyz, idx, weights, scales, shifts, precision):
+def _(xyz, feats, new_xyz, idx, packed, couts, precision):
     S = 1 if idx is None else idx.shape[1]
-    return xyz.new_empty(xyz.shape[0], weights[2].shape[0], S, dtype=torch.float32)
+    return xyz.new_empty(xyz.shape[0], S, couts[2], dtype=torch.float32)
 
 
 # --------------------------------------------------------------------------------------- NN-min

@@ -270,6 +270,33 @@ def test_encoder_bf16_tensor_core_path(api, dev, golden):
     np.testing.assert_allclose(feat.cpu().numpy(), g["feature"], rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("precision,rtol,atol", [(0, 1e-4, 1e-5), (1, 2e-2, 2e-2)])
+@pytest.mark.parametrize("feature_dim", [512, 256, 96])
+def test_encoder_feature_dims_and_batches_against_oracle(api, dev, oracle, precision, rtol, atol, feature_dim):
+    """The group_all stage (259 -> 256 -> 512 -> F) at the reference's default F = 512 (layer 1 and layer 2
+    both cut into halves on the tensor-core path), F = 256 (the diffusion model's) and an F that needs
+    channel padding, on a batch of 3 scans: the whole encoder against the oracle."""
+    torch.manual_seed(21)
+    enc = api.enc.PointNet2Encoder(feature_dim=feature_dim, mlp_precision=precision).to(dev)
+    g = torch.Generator().manual_seed(8)
+    for mod in enc.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+    enc.eval()
+    x = S.uniform_cloud(31, 3, 2500)
+    torch.manual_seed(77)
+    s1 = torch.randint(0, 2500, (3,), dtype=torch.long).numpy()
+    s2 = torch.randint(0, 512, (3,), dtype=torch.long).numpy()
+    torch.manual_seed(77)
+    with torch.no_grad():
+        feat = enc(x.to(dev))
+    assert feat.shape == (3, feature_dim)
+    sd = {k: v.detach().cpu().numpy() for k, v in enc.state_dict().items()}
+    ref = oracle.encoder_forward(x.numpy(), sd, s1, s2)
+    np.testing.assert_allclose(feat.cpu().numpy(), ref["feature"], rtol=rtol, atol=atol)
+
+
 def test_sa_mlp_tensor_core_ragged_groups(api, dev, oracle):
     """K not a multiple of 32 and a partial last row tile exercise the per-element pooling path."""
     torch.manual_seed(0)
