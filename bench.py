@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--mlp-precision", type=int, default=int(os.environ.get("PCST_MLP_PRECISION", "1")),
                     help="1 = bf16 tcgen05 shared MLP (north_star's design, default); 0 = fp32 CUDA-core MLP")
     ap.add_argument("--chamfer-steps", type=int, default=5)
+    ap.add_argument("--batched-scans", type=int, default=8, help="scans per GPU of the secondary batched-throughput line (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -257,6 +258,31 @@ def main():
         ms_ch = timed(lambda: chamfer_distance_chunked_optimized(x_dev, y_dev), max(1, args.chamfer_steps))
     ch_ms = max(statistics.mean(ms_ch), 1e-9)
 
+    # ---- batched throughput: 8 scans per GPU in one graph (FPS = 8 concurrent 16-CTA clusters, one per GPC) ----
+    batched = None
+    if args.batched_scans > 1:
+        xb = torch.cat([S.lidar_scan((rank * args.batched_scans + i) % 16) for i in range(args.batched_scans)], 0).to(dev)
+        for _ in range(3):
+            genc(xb)
+        ms_b = timed(lambda: genc(xb), max(3, K // 2))
+        batched = statistics.mean(ms_b)
+        del xb
+
+    # ---- N > 1: ONE 120k x 120k Chamfer with the query points sharded over the ranks (BASELINE config 5):
+    # all-gather of the target cloud + one sweep of the local [N/G x M] tile + MIN all-reduce of the column minima
+    ch_sharded = None
+    if world > 1:
+        from pointcloud_style_transfer_b200 import distributed as D
+        p_full, t_full = S.lidar_scan(0), S.lidar_scan(100)
+        lo, hi = D.slice_of_rank(N_POINTS, world, rank)
+        p_loc, t_loc = p_full[:, lo:hi].contiguous().to(dev), t_full[:, lo:hi].contiguous().to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                cd_sh = D.chamfer_query_sharded_one_sweep(p_loc, t_loc)
+            ms_sh = timed(lambda: D.chamfer_query_sharded_one_sweep(p_loc, t_loc), max(1, args.chamfer_steps))
+            cd_one = chamfer_distance_chunked_optimized(p_full.to(dev), t_full.to(dev))
+        ch_sharded = (statistics.mean(ms_sh), float((cd_sh - cd_one).abs().max() / cd_one.abs().max()))
+
     def allmax(v):
         if world == 1:
             return v
@@ -268,6 +294,8 @@ def main():
     t_e2e = allmax(sum(ms_e2e)) / K
     t_ch = allmax(ch_ms)
     fps_ms_max = allmax(fps_ms)
+    t_b = allmax(batched) if batched is not None else None
+    t_sh = allmax(ch_sharded[0]) if ch_sharded is not None else None
 
     if rank == 0:
         value = world * N_POINTS / (t_dev * 1e-3)
@@ -304,6 +332,16 @@ def main():
                                      "frac_if_both_directions_counted": 2 * ch_tflops / fp32_peak}},
             "clocks": clocks,
         }
+        if t_b is not None:
+            line["batched"] = {"metric": "SA points/sec, %d x 120k-pt scans per GPU in one graph" % args.batched_scans,
+                               "value": world * args.batched_scans * N_POINTS / (t_b * 1e-3), "unit": "points/s",
+                               "ms_per_step": t_b, "scans_per_gpu": args.batched_scans}
+        if t_sh is not None:
+            line["chamfer_query_sharded"] = {
+                "metric": "Chamfer NN pairs/sec, ONE 120k x 120k pair, query points sharded over %d GPUs" % world,
+                "value": pairs / (t_sh * 1e-3), "unit": "pairs/s", "ms_per_call": t_sh, "scaling": "strong",
+                "collectives": "all-gather target (1.44 MB), all-reduce MIN of 120k column minima, all-reduce SUM of row sums",
+                "rel_diff_vs_single_gpu": ch_sharded[1]}
         if not args.no_cpu_baseline and world == 1:
             times, cores = cpu_encoder_baseline(budget_s=10.0)
             line["cpu_baseline"] = {"value": N_POINTS / statistics.mean(times), "unit": "points/s", "cores": cores,

@@ -51,6 +51,11 @@ int pcst_device_check(void);
 int pcst_set_tuning(const char* key, int value);
 int pcst_get_tuning(const char* key, int* value);
 
+/* Warm the L2 cache with [ptr, ptr + bytes) (one prefetch per 128-byte line; returns immediately, stream-ordered).
+ * The encoder uses it to pull the packed MLP weights of all three stages into the 126 MB L2 on a parallel
+ * stream while the first FPS runs on 16 of the 148 SMs; no reference counterpart (a scheduling aid, not arithmetic). */
+int pcst_l2_prefetch(const void* ptr, size_t bytes, pcst_stream_t stream);
+
 /* ---- farthest_point_sample: models/pointnet2_encoder.py:30-45 --------------------------------
  * xyz [B,N,3]; start [B] = the start index per cloud (the reference draws it with torch.randint
  * on the CPU generator, :36 -- that draw stays in the caller); out [B,npoint] int64.

@@ -65,6 +65,12 @@ __global__ void pack_points_kernel(const float* __restrict__ xyz, int N, int Npa
     }
 }
 
+// ---- L2 prefetch: one prefetch.global.L2 per 128-byte line --------------------------------------
+__global__ void l2_prefetch_kernel(const unsigned char* __restrict__ p, size_t bytes) {
+    const size_t line = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128;
+    if (line < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + line));
+}
+
 int launch_pack(const float* xyz, int B, int N, int Npad, float4* out, cudaStream_t stream) {
     int blocks = (Npad + 255) / 256;
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
@@ -93,6 +99,14 @@ int pcst_device_check(void) {
         return PCST_ERR_UNSUPPORTED;
     }
     return PCST_OK;
+}
+
+int pcst_l2_prefetch(const void* ptr, size_t bytes, pcst_stream_t stream_) {
+    if (!ptr || bytes == 0) return PCST_OK;
+    const size_t lines = (bytes + 127) / 128;
+    const unsigned blocks = (unsigned)((lines + 255) / 256);
+    pcst::l2_prefetch_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>((const unsigned char*)ptr, bytes);
+    return pcst::check_cuda(cudaGetLastError(), "l2_prefetch_kernel");
 }
 
 int pcst_set_tuning(const char* key, int value) {

@@ -2,7 +2,7 @@
 //
 // The reference materialises an int64 [B,S,N] index tensor and a fp32 [B,S,N] distance matrix and
 // sorts the former along N.  Here the same full S x N sweep is done in two small kernels:
-//   1. bq_mask_kernel: CTA = (candidate tile of 1024 points) x (128 queries).  The tile's raw xyz rows
+//   1. bq_mask_kernel: CTA = (candidate tile of 1024 points) x (256 queries, two per thread as fp32x2 pairs).  The tile's raw xyz rows
 //      (12 KiB) are staged in shared memory by one 1-D TMA bulk copy, repacked there to float4
 //      (x, y, z, |p|^2) and broadcast to all threads; each thread owns one query and evaluates the
 //      predicate NOT(D > r^2) in the reference's exact fp32 rounding (D = ((-2*dot) + |q|^2) + |p|^2,
@@ -58,18 +58,22 @@ __device__ __forceinline__ bool bq_inside(float qx, float qy, float qz, float qn
     return !(d > radius_sq);
 }
 
+// Each thread owns TWO queries (s and s + 128) held as fp32x2 register pairs, so one packed FMUL2 / FFMA2 /
+// FADD2 evaluates the candidate against both (the candidate's components are the broadcast scalar operand);
+// 32 candidates fill one mask word per query, four words go out as one 128-bit store.
+constexpr int kBQQueriesPerCta = 2 * kBQThreads;
+
 __global__ void __launch_bounds__(kBQThreads)
 bq_mask_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int Npad, int S,
                float radius_sq, unsigned int* __restrict__ mask) {
     __shared__ __align__(128) float4 tile[kTilePoints];
     __shared__ __align__(128) float raw[kTilePoints * 3];
-    __shared__ unsigned int words[kBQThreads][33];
     __shared__ __align__(8) uint64_t full_bar;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int t = blockIdx.x;  // candidate tile
     const int b = blockIdx.z;
-    const int s = blockIdx.y * kBQThreads + tid;
+    const int s0 = blockIdx.y * kBQQueriesPerCta + tid, s1 = s0 + kBQThreads;
     const int words_per_row = Npad / 32;
 
     if (tid == 0) {
@@ -77,31 +81,45 @@ bq_mask_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
         fence_mbar_init();
     }
     __syncthreads();
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (s < S) {
-        const float* q = new_xyz + ((size_t)b * S + s) * 3;
-        qx = q[0]; qy = q[1]; qz = q[2];
+    float2 qx = make_float2(0.f, 0.f), qy = qx, qz = qx;
+    if (s0 < S) {
+        const float* q = new_xyz + ((size_t)b * S + s0) * 3;
+        qx.x = q[0]; qy.x = q[1]; qz.x = q[2];
     }
-    const float qn = norm3_sq(qx, qy, qz);
+    if (s1 < S) {
+        const float* q = new_xyz + ((size_t)b * S + s1) * 3;
+        qx.y = q[0]; qy.y = q[1]; qz.y = q[2];
+    }
+    const float2 qn = make_float2(norm3_sq(qx.x, qy.x, qz.x), norm3_sq(qx.y, qy.y, qz.y));
     int n = N - t * kTilePoints;
     if (n > kTilePoints) n = kTilePoints;
     bq_stage_tile(xyz + ((size_t)b * N + (size_t)t * kTilePoints) * 3, n, raw, tile, &full_bar, 0);
 
+    unsigned int* row0 = mask + ((size_t)b * S + s0) * words_per_row + (size_t)t * 32;
+    unsigned int* row1 = mask + ((size_t)b * S + s1) * words_per_row + (size_t)t * 32;
 #pragma unroll 1
-    for (int c = 0; c < kTilePoints / 32; ++c) {
-        unsigned int w = 0;
+    for (int c4 = 0; c4 < kTilePoints / 128; ++c4) {
+        unsigned int w0[4], w1[4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float4 p = tile[c * 32 + i];  // same address for every thread: shared-memory broadcast
-            w |= (bq_inside(qx, qy, qz, qn, p, radius_sq) ? 1u : 0u) << i;
+        for (int k = 0; k < 4; ++k) {
+            unsigned int a0 = 0, a1 = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float4 p = tile[c4 * 128 + k * 32 + i];  // same address for every thread: broadcast
+                // D = ((-2 * dot) + |q|^2) + |p|^2 with dot = fma(qz,pz, fma(qy,py, qx*px)) (pointnet2_encoder.py:12-14)
+                const float2 px = make_float2(p.x, p.x), py = make_float2(p.y, p.y), pz = make_float2(p.z, p.z);
+                float2 d = __ffma2_rn(qz, pz, __ffma2_rn(qy, py, __fmul2_rn(qx, px)));
+                d = __fmul2_rn(d, make_float2(-2.0f, -2.0f));  // exact scaling
+                d = __fadd2_rn(d, qn);
+                d = __fadd2_rn(d, make_float2(p.w, p.w));      // sentinel rows have |p|^2 = +inf -> never inside
+                a0 |= (d.x > radius_sq ? 0u : 1u) << i;
+                a1 |= (d.y > radius_sq ? 0u : 1u) << i;
+            }
+            w0[k] = a0;
+            w1[k] = a1;
         }
-        words[tid][c] = w;
-    }
-    __syncthreads();
-    // coalesced write-out: each warp stores 32 query rows of 32 words (128 B) each
-    for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-        const int sq = blockIdx.y * kBQThreads + r;
-        if (sq < S) mask[((size_t)b * S + sq) * words_per_row + (size_t)t * 32 + lane] = words[r][lane];
+        if (s0 < S) *reinterpret_cast<uint4*>(row0 + c4 * 4) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+        if (s1 < S) *reinterpret_cast<uint4*>(row1 + c4 * 4) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
     }
 }
 
@@ -268,7 +286,7 @@ extern "C" int pcst_ball_query_f32(const float* xyz, const float* new_xyz, int B
     }
     const int Npad = padded_points(N);
     unsigned int* mask = (unsigned int*)ws;
-    const int qblocks = (S + kBQThreads - 1) / kBQThreads;
+    const int qblocks = (S + kBQQueriesPerCta - 1) / kBQQueriesPerCta;
     PCST_CHECK_ARG(qblocks <= 65535, "S too large");
     bq_mask_kernel<<<dim3(Npad / kTilePoints, qblocks, B), kBQThreads, 0, stream>>>(xyz, new_xyz, N, Npad, S, radius_sq,
                                                                                     mask);

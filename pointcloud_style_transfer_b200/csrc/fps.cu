@@ -156,7 +156,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
             // ---- exact skip test (warp-uniform) ----
             const float gx = box_gap(lox, hix, cx), gy = box_gap(loy, hiy, cy), gz = box_gap(loz, hiz, cz);
             const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-            if ((prune && lb >= __int_as_float(cmax)) || (prune == 3 && it > 0)) {
+            if ((prune && lb >= __int_as_float(cmax)) || (prune >= 3 && it > 0)) {
                 wmax = cmax;
                 widx = cidx;
             } else {
@@ -199,7 +199,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         // ---- block argmax, computed redundantly by every warp ----
         int bmax = wmax;
         unsigned bidx = widx;
-        if (nwarps > 1) {
+        if (nwarps > 1 && prune != 4) {
             if (lane == 0) sh.wslot[par][warp] = make_int2(wmax, (int)widx);
             __syncthreads();
             int2 e = lane < nwarps ? sh.wslot[par][lane] : make_int2((int)0x80000000, (int)kNoIdx);
@@ -209,7 +209,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         // shared-memory slot of the block's best point (P > 0)
         const int bslot = P > 0 ? (int)((bidx / CH) >> log2c) * CH + (int)(bidx % CH) : 0;
 
-        if (C == 1) {
+        if (C == 1 || prune == 5) {
             far = bidx;
             if (P > 0) {
                 cx = sx[bslot]; cy = sy[bslot]; cz = sz[bslot];
@@ -279,7 +279,8 @@ static FpsPlan fps_plan(int B, int N) {
     if (C < 1) C = 1;
     p.C = C;
     int threads = tuning("fps.threads", 0);
-    if (threads == 0) threads = (C == 1 && N <= 512) ? 32 : ((C == 1 && N <= 2048) ? 128 : kFpsMaxThreads);
+    // measured (B200, 512 -> 128): 128 threads 63 us, 32 threads 72 us, 512 threads 65 us per launch
+    if (threads == 0) threads = (C == 1 && N <= 64) ? 32 : ((C == 1 && N <= 2048) ? 128 : kFpsMaxThreads);
     if (threads != 32 && threads != 128) threads = kFpsMaxThreads;
     p.threads = threads;
     const long lanes = (long)threads * C;                 // threads that share one cloud
@@ -312,7 +313,8 @@ static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoi
     cfg.numAttrs = 1;
     int pts_per_cta = p.pts_per_cta;
     // 2 = off (for A/B measurements); 3 = skip every chunk after the first iteration (WRONG results:
-    // measures the latency floor of the exchange chain alone)
+    // measures the latency floor of the exchange chain alone); 4 = 3 without the block-level reduction;
+    // 5 = 3 without the cluster exchange (latency probes, results invalid)
     int prune = tuning("fps.prune", 1);
     prune = prune == 2 ? 0 : prune;
     int log2c = 0;

@@ -50,7 +50,7 @@ def _workspace(nbytes: int, device) -> Tensor:
 
 # Launch accounting and optional per-op CUDA-event timing (used by bench.py for `gpu_launches` and the
 # roofline's live kernel durations).  KERNELS_PER_CALL counts __global__ launches (memsets excluded).
-KERNELS_PER_CALL = {"pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
+KERNELS_PER_CALL = {"pcst_l2_prefetch": 1, "pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
                     "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 7, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
                     "pcst_knn_interpolate_f32": 1}
@@ -86,6 +86,13 @@ def _call(name: str, *args, kernels: Optional[int] = None) -> None:
         b.record()
         _event_log.append((name, a, b))
     launch_count += KERNELS_PER_CALL[name] if kernels is None else kernels
+
+
+def l2_prefetch(t: Tensor) -> None:
+    """Stream-ordered L2 warm-up of a (contiguous) CUDA tensor's bytes; a scheduling aid, no result."""
+    _need_cuda(t)
+    with torch.cuda.device(t.device):
+        _call("pcst_l2_prefetch", _p(t), t.numel() * t.element_size(), _stream())
 
 
 # ------------------------------------------------------------------------------------------ FPS

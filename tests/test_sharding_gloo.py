@@ -25,6 +25,13 @@ def _oracle_nn_min(a, b, form):
     return torch.from_numpy(O.nn_min(a.numpy(), b.numpy(), form))
 
 
+def _oracle_pair(a, b, form):
+    from oracle import ref_oracle as O
+    rows = O.nn_min(a.numpy(), b.numpy(), 0 if form == 0 else 1)
+    cols = O.nn_min(b.numpy(), a.numpy(), 0 if form == 0 else 2)
+    return torch.from_numpy(rows), torch.from_numpy(cols)
+
+
 class _ToyEncoder(torch.nn.Module):
     def forward(self, x):  # [S,N,3] -> [S,4]: any per-scan function will do for the plumbing test
         return torch.cat([x.mean(dim=1), x.abs().amax(dim=(1, 2))[:, None]], dim=1)
@@ -42,9 +49,14 @@ def _worker(rank, world, port, q):
         ok_gather = torch.equal(g, pred)
         cd = D.chamfer_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), nn_min_fn=_oracle_nn_min)
         cdm = D.chamfer_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), nn_min_fn=_oracle_nn_min, form=1)
+        cd1 = D.chamfer_query_sharded_one_sweep(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair)
+        cdm1 = D.chamfer_query_sharded_one_sweep(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair, form=1)
+        # a rank with an EMPTY query slice (more ranks than points would do this): rank 1 holds no pred points
+        elo, ehi = (0, 5) if rank == 0 else (5, 5)
+        cde = D.chamfer_query_sharded_one_sweep(pred[:, :5][:, elo:ehi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair)
         scans = S.uniform_cloud(5, 5, 64)
         feats = D.encode_scans_sharded(_ToyEncoder(), scans)
-        q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy()))
+        q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy(), cd1.numpy(), cdm1.numpy(), cde.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -65,10 +77,14 @@ def test_query_sharded_chamfer_and_scan_sharding_world2(oracle):
     refm = oracle.metrics_chamfer_distance(pred.numpy(), target.numpy())
     scans = S.uniform_cloud(5, 5, 64)
     ref_feats = _ToyEncoder()(scans).numpy()
-    for rank, ok_gather, cd, cdm, feats in res:
+    ref_e = oracle.chamfer_distance_chunked_optimized(pred.numpy()[:, :5], target.numpy())
+    for rank, ok_gather, cd, cdm, feats, cd1, cdm1, cde in res:
         assert ok_gather
         np.testing.assert_allclose(cd, ref, rtol=1e-6)
         np.testing.assert_allclose(cdm, refm, rtol=1e-6)
+        np.testing.assert_allclose(cd1, ref, rtol=1e-6)     # one sweep + MIN all-reduce of the column minima
+        np.testing.assert_allclose(cdm1, refm, rtol=1e-6)
+        np.testing.assert_allclose(cde, ref_e, rtol=1e-6)   # empty slice on one rank
         np.testing.assert_array_equal(feats, ref_feats)
 
 

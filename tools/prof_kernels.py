@@ -31,6 +31,12 @@ def timeit(name, fn, reps=5):
     print(f"{name}: {a.elapsed_time(b) / reps * 1e3:.1f} us", flush=True)
 
 
+if "fpsprobe" in which:
+    from pointcloud_style_transfer_b200 import _lib
+    for mode, label in ((0, "full"), (3, "skip all chunks"), (4, "skip all, no block reduction"), (5, "skip all, no cluster exchange")):
+        _lib.set_tuning("fps.prune", mode)
+        timeit(f"fps 120k->512 probe [{label}]", lambda: ops.fps(x, 512, start), reps=10)
+    _lib.set_tuning("fps.prune", 0)
 if "fps" in which:
     from pointcloud_style_transfer_b200 import _lib
     timeit("fps 120k->512 (lidar order)", lambda: ops.fps(x, 512, start))
@@ -38,6 +44,10 @@ if "fps" in which:
     timeit("fps 120k->512 (lidar order, no skip test)", lambda: ops.fps(x, 512, start))
     _lib.set_tuning("fps.prune", 3)
     timeit("fps 120k->512 (exchange chain only: every chunk skipped, results invalid)", lambda: ops.fps(x, 512, start))
+    _lib.set_tuning("fps.prune", 4)
+    timeit("fps 120k->512 (probe: chain without the block-level reduction)", lambda: ops.fps(x, 512, start))
+    _lib.set_tuning("fps.prune", 5)
+    timeit("fps 120k->512 (probe: chain without the cluster exchange)", lambda: ops.fps(x, 512, start))
     _lib.set_tuning("fps.prune", 0)
     xu = S.uniform_cloud(0, 1, 120000).to(dev)
     timeit("fps 120k->512 (uniform random order)", lambda: ops.fps(xu, 512, start))
