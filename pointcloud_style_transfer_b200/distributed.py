@@ -29,15 +29,22 @@ def slice_of_rank(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def all_gather_ragged(x: torch.Tensor, group=None) -> torch.Tensor:
-    """All-gather [B, n_r, C] shards with different n_r along dim 1 -> [B, sum n_r, C] in rank order."""
+def all_gather_ragged(x: torch.Tensor, group=None, total: Optional[int] = None) -> torch.Tensor:
+    """All-gather [B, n_r, C] shards with different n_r along dim 1 -> [B, sum n_r, C] in rank order.
+    ``total`` (optional): the global point count when the shards are the ``slice_of_rank`` partition of it --
+    the shard sizes are then known without a size exchange (no host synchronisation)."""
     world = dist.get_world_size(group)
     if world == 1:
         return x
-    n = torch.tensor([x.shape[1]], dtype=torch.long, device=x.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if total is not None:
+        sizes = [hi - lo for lo, hi in (slice_of_rank(total, world, r) for r in range(world))]
+        if sizes[dist.get_rank(group)] != x.shape[1]:
+            raise ValueError("all_gather_ragged: the local shard is not the slice_of_rank partition of `total`")
+    else:
+        n = torch.tensor([x.shape[1]], dtype=torch.long, device=x.device)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=group)
+        sizes = [int(s.item()) for s in sizes]
     nmax = max(sizes)
     pad = x.new_zeros(x.shape[0], nmax, x.shape[2])
     pad[:, : x.shape[1]] = x
@@ -79,16 +86,19 @@ def _default_nn_min_pair(a, b, form):
 
 
 def chamfer_query_sharded_one_sweep(pred_local: torch.Tensor, target_local: torch.Tensor, group=None,
-                                    pair_fn: Optional[Callable] = None, form: int = 0) -> torch.Tensor:
+                                    pair_fn: Optional[Callable] = None, form: int = 0,
+                                    pred_total: Optional[int] = None, target_total: Optional[int] = None) -> torch.Tensor:
     """Same result as ``chamfer_query_sharded`` with every pair evaluated ONCE across the whole job
     (SURVEY.md §8(e) variant): rank r sweeps its [n_r x M] tile of the pair matrix, which yields complete
     row minima for its pred points and PARTIAL column minima for all M target points; one
     ``all_reduce(MIN)`` over the [B,M] column minima (480 KB for a 120k-point scan) completes them.
     Exchange: all-gather of the target cloud (if it starts sharded), MIN all-reduce of M floats, SUM
-    all-reduce of B partial row sums.  An empty local slice contributes +inf column minima."""
+    all-reduce of B partial row sums.  An empty local slice contributes +inf column minima.
+    ``pred_total`` / ``target_total``: the global point counts when the shards are ``slice_of_rank``
+    partitions; with them the call issues no size exchange and no host synchronisation."""
     pair_fn = pair_fn or _default_nn_min_pair
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    target_all = all_gather_ragged(target_local, group) if world > 1 else target_local
+    target_all = all_gather_ragged(target_local, group, target_total) if world > 1 else target_local
     B, M = target_all.shape[0], target_all.shape[1]
     if pred_local.shape[1] > 0:
         rowmin, colmin = pair_fn(pred_local, target_all, 0 if form == 0 else 1)
@@ -96,13 +106,18 @@ def chamfer_query_sharded_one_sweep(pred_local: torch.Tensor, target_local: torc
     else:
         colmin = torch.full((B, M), float("inf"), dtype=torch.float32, device=target_all.device)
         rowsum = torch.zeros(B, dtype=torch.float64, device=target_all.device)
-    n_total = torch.tensor([pred_local.shape[1]], dtype=torch.long, device=target_all.device)
+    n_total = pred_total
     if world > 1:
         colmin = colmin.contiguous()
         dist.all_reduce(colmin, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(rowsum, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(n_total, op=dist.ReduceOp.SUM, group=group)
-    out = rowsum / int(n_total.item()) + colmin.double().sum(dim=1) / M
+        if n_total is None:
+            cnt = torch.tensor([pred_local.shape[1]], dtype=torch.long, device=target_all.device)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+            n_total = int(cnt.item())
+    elif n_total is None:
+        n_total = pred_local.shape[1]
+    out = rowsum / n_total + colmin.double().sum(dim=1) / M
     if form != 0:
         out = out / 2
     return out.float()

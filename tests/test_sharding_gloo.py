@@ -50,7 +50,8 @@ def _worker(rank, world, port, q):
         cd = D.chamfer_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), nn_min_fn=_oracle_nn_min)
         cdm = D.chamfer_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), nn_min_fn=_oracle_nn_min, form=1)
         cd1 = D.chamfer_query_sharded_one_sweep(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair)
-        cdm1 = D.chamfer_query_sharded_one_sweep(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair, form=1)
+        cdm1 = D.chamfer_query_sharded_one_sweep(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair, form=1,
+                                                 pred_total=1001, target_total=777)  # known totals: no size exchange
         # a rank with an EMPTY query slice (more ranks than points would do this): rank 1 holds no pred points
         elo, ehi = (0, 5) if rank == 0 else (5, 5)
         cde = D.chamfer_query_sharded_one_sweep(pred[:, :5][:, elo:ehi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair)
