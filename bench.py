@@ -154,7 +154,8 @@ def main():
     ap.add_argument("--mlp-precision", type=int, default=int(os.environ.get("PCST_MLP_PRECISION", "1")),
                     help="1 = bf16 tcgen05 shared MLP (north_star's design, default); 0 = fp32 CUDA-core MLP")
     ap.add_argument("--chamfer-steps", type=int, default=5)
-    ap.add_argument("--batched-scans", type=int, default=8, help="scans per GPU of the secondary batched-throughput line (0 = skip)")
+    ap.add_argument("--batched-scans", type=int, default=-1,
+                    help="scans per GPU of the secondary batched-throughput line (0 = skip, -1 = as many as FPS clusters fit at once)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -266,6 +267,9 @@ def main():
 
     # ---- batched throughput: 8 scans per GPU in one graph (FPS = 8 concurrent 16-CTA clusters, one per GPC) ----
     batched = None
+    if args.batched_scans < 0:  # auto: as many scans as the FPS clusters that fit the GPU at once
+        from pointcloud_style_transfer_b200 import _lib
+        args.batched_scans = max(2, min(8, _lib.load().pcst_fps_max_concurrent_clouds(N_POINTS)))
     if args.batched_scans > 1:
         xb = torch.cat([S.lidar_scan((rank * args.batched_scans + i) % 16) for i in range(args.batched_scans)], 0).to(dev)
         for _ in range(3):
@@ -340,7 +344,7 @@ def main():
             "clocks": clocks,
         }
         if t_b is not None:
-            line["batched"] = {"metric": "SA points/sec, %d x 120k-pt scans per GPU in one graph" % args.batched_scans,
+            line["batched"] = {"metric": "SA points/sec, %d x 120k-pt scans per GPU in one graph (= concurrent 16-CTA FPS clusters)" % args.batched_scans,
                                "value": world * args.batched_scans * N_POINTS / (t_b * 1e-3), "unit": "points/s",
                                "ms_per_step": t_b, "scans_per_gpu": args.batched_scans}
         if t_sh is not None:

@@ -63,6 +63,9 @@ int pcst_l2_prefetch(const void* ptr, size_t bytes, pcst_stream_t stream);
  * index_points(xyz, fps_idx) of SetAbstraction.forward (:92), at no extra cost.
  * One persistent thread-block cluster per cloud; points and running distances stay on chip. */
 size_t pcst_fps_workspace_bytes(int B, int N, int npoint);
+/* Number of N-point clouds the current device processes concurrently (one cluster each); larger batches run in
+ * waves.  0 on error.  A scheduling hint for callers that batch scans; no reference counterpart. */
+int pcst_fps_max_concurrent_clouds(int N);
 int pcst_fps_f32(const float* xyz, int B, int N, int npoint, const int64_t* start, int64_t* out,
                  float* new_xyz, void* ws, size_t ws_bytes, pcst_stream_t stream);
 
@@ -123,12 +126,17 @@ typedef struct {
     const float* shift[3];
     int cout[3];
 } pcst_mlp3_t;
-size_t pcst_sa_mlp_packed_bytes(int D, const int* cout /*[3]*/, int precision);
-int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision, void* packed, size_t packed_bytes,
+/* cluster: CTAs per 128-row tile on the tensor-core path (1, 2, 4 or 8): stages with few rows (the group_all stage is
+ * one tile per scan) split every layer's output channels over a thread-block cluster.  pcst_sa_mlp_pick_cluster returns
+ * the value to use for a shape (1 for the fp32 path); the packed layout depends on it, so callers cache one blob per
+ * (precision, cluster). */
+int pcst_sa_mlp_pick_cluster(int B, int S, int K, int D, const int* cout /*[3]*/, int precision);
+size_t pcst_sa_mlp_packed_bytes(int D, const int* cout /*[3]*/, int precision, int cluster);
+int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision, int cluster, void* packed, size_t packed_bytes,
                          pcst_stream_t stream);
 size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision);
 int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
-                        int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision,
+                        int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision, int cluster,
                         const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream);
 
 /* ---- nearest-neighbour minimum reduction ------------------------------------------------------

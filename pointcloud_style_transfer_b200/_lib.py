@@ -38,6 +38,7 @@ SIGNATURES = {
     "pcst_get_tuning": (c_int, [c_char_p, POINTER(c_int)]),
     "pcst_l2_prefetch": (c_int, [c_void_p, c_size_t, c_void_p]),
     "pcst_fps_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcst_fps_max_concurrent_clouds": (c_int, [c_int]),
     "pcst_fps_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pcst_ball_query_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_ball_query_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
@@ -47,11 +48,12 @@ SIGNATURES = {
     "pcst_index_points_bwd_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pcst_group_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                c_void_p]),
-    "pcst_sa_mlp_packed_bytes": (c_size_t, [c_int, POINTER(c_int), c_int]),
-    "pcst_sa_mlp_pack_f32": (c_int, [POINTER(Mlp3), c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pcst_sa_mlp_pick_cluster": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), c_int]),
+    "pcst_sa_mlp_packed_bytes": (c_size_t, [c_int, POINTER(c_int), c_int, c_int]),
+    "pcst_sa_mlp_pack_f32": (c_int, [POINTER(Mlp3), c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pcst_sa_mlp_max_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int]),
     "pcst_sa_mlp_max_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                    POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                    POINTER(c_int), c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pcst_nn_min_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_nn_min_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),

@@ -333,6 +333,44 @@ extern "C" size_t pcst_fps_workspace_bytes(int B, int N, int npoint) {
     return fps_plan(B, N).ws;
 }
 
+// How many clouds of N points the device runs CONCURRENTLY (one cluster each): a batch larger than this
+// takes a second wave of clusters.  cudaOccupancyMaxActiveClusters accounts for the GPC-local placement of the
+// 16-CTA clusters (148 SMs do not hold nine, and not every GPC holds one).
+template <int P>
+static int fps_max_clusters(const FpsPlan& p) {
+    auto kern = fps_kernel<P>;
+    if (p.smem > 32 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
+        return 0;
+    if (p.C > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.C);
+    cfg.blockDim = dim3(p.threads);
+    cfg.dynamicSmemBytes = p.smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int pcst_fps_max_concurrent_clouds(int N) {
+    if (N <= 0) return 0;
+    const FpsPlan p = fps_plan(1, N);
+    switch (p.P) {
+        case 2: return fps_max_clusters<2>(p);
+        case 4: return fps_max_clusters<4>(p);
+        case 8: return fps_max_clusters<8>(p);
+        case 16: return fps_max_clusters<16>(p);
+        default: return fps_max_clusters<0>(p);
+    }
+}
+
 extern "C" int pcst_fps_f32(const float* xyz, int B, int N, int npoint, const int64_t* start, int64_t* out,
                             float* new_xyz, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -152,10 +152,11 @@ mlp_layer_kernel(const LayerArgs a) {
 }
 
 bool sa_mlp_tc_supported(int D, const int* cout);
-size_t sa_mlp_tc_blob_bytes(int D, const int* cout);
-int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, void* blob, cudaStream_t stream);
+int sa_mlp_tc_pick_cluster(long tiles, int D, const int* cout);
+size_t sa_mlp_tc_blob_bytes(int D, const int* cout, int C);
+int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, int C, void* blob, cudaStream_t stream);
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
-                  int K, int D, const int* cout, const void* blob, float* out, cudaStream_t stream);
+                  int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream);
 
 // fp32 blob: w0 [n0, 3+D] | w1 [n1, n0] | w2 [n2, n1] | scale0 shift0 scale1 shift1 scale2 shift2, each 256-byte aligned
 struct F32Blob {
@@ -194,21 +195,29 @@ static int check_cout(const int* cout) {
 // fp32 path, which is the more precise of the two
 static bool use_tc(int D, const int* cout, int precision) { return precision == 1 && sa_mlp_tc_supported(D, cout); }
 
-extern "C" size_t pcst_sa_mlp_packed_bytes(int D, const int* cout, int precision) {
-    if (D < 0 || !check_cout(cout)) return 0;
-    return use_tc(D, cout, precision) ? sa_mlp_tc_blob_bytes(D, cout) : f32_blob(D, cout).total;
+extern "C" int pcst_sa_mlp_pick_cluster(int B, int S, int K, int D, const int* cout, int precision) {
+    if (B <= 0 || S <= 0 || K <= 0 || D < 0 || !check_cout(cout) || !use_tc(D, cout, precision)) return 1;
+    const long tiles = ((long)B * S * K + 127) / 128;
+    return sa_mlp_tc_pick_cluster(tiles, D, cout);
 }
 
-extern "C" int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision, void* packed, size_t packed_bytes,
-                                    pcst_stream_t stream_) {
+extern "C" size_t pcst_sa_mlp_packed_bytes(int D, const int* cout, int precision, int cluster) {
+    if (D < 0 || !check_cout(cout)) return 0;
+    return use_tc(D, cout, precision) ? sa_mlp_tc_blob_bytes(D, cout, cluster) : f32_blob(D, cout).total;
+}
+
+extern "C" int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision, int cluster, void* packed,
+                                    size_t packed_bytes, pcst_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PCST_CHECK_ARG(mlp && packed, "null pointer");
     PCST_CHECK_ARG(D >= 0 && check_cout(mlp->cout), "Cout must be a multiple of 32 in [32, 1024]");
     for (int l = 0; l < 3; ++l) PCST_CHECK_ARG(mlp->w[l] && mlp->scale[l] && mlp->shift[l], "null layer pointer");
     PCST_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16 tensor cores)");
-    PCST_CHECK_ARG(packed_bytes >= pcst_sa_mlp_packed_bytes(D, mlp->cout, precision) && ((uintptr_t)packed & 255) == 0,
+    const size_t need_bytes = pcst_sa_mlp_packed_bytes(D, mlp->cout, precision, cluster);
+    PCST_CHECK_ARG(need_bytes > 0, "unsupported layer widths / cluster size");
+    PCST_CHECK_ARG(packed_bytes >= need_bytes && ((uintptr_t)packed & 255) == 0,
                    "packed buffer too small or not 256-byte aligned");
-    if (use_tc(D, mlp->cout, precision)) return sa_mlp_tc_pack(mlp, D, packed, stream);
+    if (use_tc(D, mlp->cout, precision)) return sa_mlp_tc_pack(mlp, D, cluster, packed, stream);
     const F32Blob b = f32_blob(D, mlp->cout);
     int cin = 3 + D;
     for (int l = 0; l < 3; ++l) {
@@ -229,7 +238,7 @@ extern "C" size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, in
 }
 
 extern "C" int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
-                                   int B, int N, int S, int K, int D, const int* cout, int precision,
+                                   int B, int N, int S, int K, int D, const int* cout, int precision, int cluster,
                                    const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PCST_CHECK_ARG(xyz && out && packed, "null pointer");
@@ -240,7 +249,8 @@ extern "C" int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const f
     PCST_CHECK_ARG(!idx || new_xyz, "new_xyz is required with idx");
     PCST_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16 tensor cores)");
     PCST_CHECK_ARG(((uintptr_t)packed & 255) == 0, "packed must be 256-byte aligned");
-    if (use_tc(D, cout, precision)) return sa_mlp_tc_run(xyz, feats, new_xyz, idx, B, N, S, K, D, cout, packed, out, stream);
+    if (use_tc(D, cout, precision))
+        return sa_mlp_tc_run(xyz, feats, new_xyz, idx, B, N, S, K, D, cout, cluster, packed, out, stream);
 
     const size_t need = pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, cout, precision);
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 255)) {

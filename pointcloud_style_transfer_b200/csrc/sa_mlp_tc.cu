@@ -17,6 +17,13 @@
 // Layers wider than 256 (the group_all stage: 259 -> 256 -> 512 -> F) are cut into N halves whose
 // outputs feed the next layer as K halves accumulating into the same TMEM columns, so the widest
 // operand in shared memory stays 128 x 272 bf16 and the accumulators fit the 512 TMEM columns.
+// Stages with few row tiles (the group_all stage is ONE tile per scan) are additionally split along N over a
+// thread-block cluster of C = 2/4/8 CTAs: every CTA holds the same 128 rows and computes an N/C slice of each
+// step, so the weight stream, the MMAs and the epilogues all shrink by C.  After an epilogue a CTA pushes its
+// bf16 activation slice (a contiguous block of the [K/8][128][8] operand) into every peer's shared memory with
+// cp.async.bulk.shared::cluster (completion counted on the peer's mbarrier), and accumulator completion is
+// multicast to all CTAs of the cluster with tcgen05.commit.multicast::cluster, which is also what makes it safe
+// to overwrite a peer's operand buffer.
 // Activations never touch HBM; weights are packed ONCE per parameter version (pcst_sa_mlp_pack_f32)
 // and cached by the caller.  Bound: tensor pipe in the limit of many rows; at the reference's shapes
 // (16 384 / 8 192 / 128 rows per scan) a stage is latency-bound.
@@ -32,7 +39,7 @@ constexpr int kTcM = 128;           // rows per CTA = TMEM lanes
 constexpr int kTcEpiThreads = 128;  // warps 0-3
 constexpr int kTcThreads = 192;     // + producer warp + MMA warp
 constexpr int kTcMaxN = 256;        // one tcgen05.mma covers a whole step's width
-constexpr int kTcChunkK = 32;       // K rows per ring stage
+constexpr int kTcStageBytes = 16 * 1024;  // ring stage: a K chunk of a step's weights, as many rows as fit
 constexpr int kTcMaxStages = 4;
 constexpr int kTcMaxSteps = 9;
 constexpr int kTcMaxBlocks = 7;
@@ -40,9 +47,11 @@ constexpr int kTcMaxBlocks = 7;
 struct TcStep {
     uint32_t a_off;     // shared-memory offset of the A operand
     uint32_t out_off;   // epi 1: shared-memory offset of the activation buffer written
-    uint32_t w_off;     // offset of this step's weight block in the packed blob
+    uint32_t w_off;     // offset of this step's weight block in the packed blob (sub-block of cluster rank 0)
+    uint32_t w_stride;  // bytes between the sub-blocks of consecutive cluster ranks
     uint16_t kp;        // reduction length (multiple of 16)
-    uint16_t n;         // output channels of the step (multiple of 16, <= 256)
+    uint16_t ck;        // K rows per weight chunk (multiple of 16): ck * n * 2 bytes <= one ring stage
+    uint16_t n;         // output channels of the step PER CTA (multiple of 16, <= 256)
     uint16_t tmem_col;  // first accumulator column
     uint16_t out_c0;    // epi 2: first output channel
     uint16_t ss_idx;    // first channel in the scale/shift tables
@@ -64,6 +73,7 @@ struct TcArgs {
     uint32_t off_ring, stage_bytes, nstages, off_ss, off_pool, tmem_cols;
     float* out;                 // [B*S, cout] point-major
     int pool_atomic;            // 0: every group lies inside one tile (plain stores); 1: atomicMax merge
+    uint32_t cluster;           // CTAs per row tile (N split); 1 = no cluster
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -92,6 +102,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+// shared::cta -> (peer) shared::cluster bulk copy, completion counted on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_cluster_addr),
+                 "r"(src_cta_addr), "r"(bytes), "r"(bar_cluster_addr)
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -138,18 +163,23 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t mma_bar;  // accumulator of an epilogue-bearing step is complete
     __shared__ __align__(8) uint64_t a_bar;    // an epilogue (or the gather) has finished: operand written, TMEM read
+    __shared__ __align__(8) uint64_t x_bar[2]; // the peers' activation slices of an epilogue have landed (by event parity)
     __shared__ uint32_t tmem_base_sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row0 = blockIdx.x * kTcM;
+    const uint32_t C = a.cluster;
+    const uint32_t rank = C > 1 ? cluster_ctarank() : 0;
+    const int row0 = (int)(blockIdx.x / C) * kTcM;
 
     if (tid == 0) {
         for (int s = 0; s < kTcMaxStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(&mma_bar, 1);
+        mbar_init(&mma_bar, C);  // every CTA of the cluster commits to every CTA's barrier
         mbar_init(&a_bar, kTcEpiThreads);
+        mbar_init(&x_bar[0], 1);
+        mbar_init(&x_bar[1], 1);
         fence_mbar_init();
     }
     if (warp == 4) {
@@ -161,6 +191,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (C > 1) cluster_sync_all();  // every peer's barriers exist before anything is sent to them
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp == 4) {
@@ -169,11 +200,11 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
             uint32_t it = 0;
             for (int s = 0; s < a.nsteps; ++s) {
                 const TcStep& st = a.st[s];
-                const unsigned char* src = a.blob + st.w_off;
-                for (int k0 = 0; k0 < st.kp; k0 += kTcChunkK, ++it) {
+                const unsigned char* src = a.blob + st.w_off + (size_t)rank * st.w_stride;
+                for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
                     const uint32_t stage = it % a.nstages;
                     if (it >= a.nstages) mbar_wait(&empty_bar[stage], ((it / a.nstages) - 1u) & 1u);
-                    const int ck = st.kp - k0 < kTcChunkK ? st.kp - k0 : kTcChunkK;
+                    const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
                     const uint32_t bytes = (uint32_t)ck * st.n * 2u;
                     mbar_arrive_expect_tx(&full_bar[stage], bytes);
                     tma_load_1d(smem + a.off_ring + stage * a.stage_bytes, src + (size_t)k0 * st.n * 2u, bytes,
@@ -185,23 +216,35 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t it = 0, seen = 0, need = 1;  // events on a_bar: the gather, then one per epilogue
+            uint32_t xseen = 0;                   // operand-writing epilogues whose REMOTE slices have been awaited
+            int xstep = 0;                        // step scanned up to while counting those epilogues
             for (int s = 0; s < a.nsteps; ++s) {
                 const TcStep& st = a.st[s];
                 while (seen < need) {
                     mbar_wait(&a_bar, seen & 1u);
                     ++seen;
                 }
+                if (C > 1) {
+                    // every operand-writing epilogue before this step: (C - 1) peers each push 128 x n x 2 bytes
+                    for (; xstep < s; ++xstep) {
+                        if (a.st[xstep].epi != 1) continue;
+                        uint64_t* xb = &x_bar[xseen & 1u];
+                        mbar_arrive_expect_tx(xb, (C - 1u) * (uint32_t)a.st[xstep].n * (kTcM * 2u));
+                        mbar_wait(xb, (xseen >> 1) & 1u);
+                        ++xseen;
+                    }
+                }
                 tc_fence_after();
                 const uint32_t idesc = umma_idesc_bf16(kTcM, st.n);
                 const uint32_t a_addr = smem_u32(smem + st.a_off);
                 const uint32_t lbo_a = kTcM * 16, lbo_w = (uint32_t)st.n * 16;
                 const uint32_t d_addr = tmem_base + st.tmem_col;
-                for (int k0 = 0; k0 < st.kp; k0 += kTcChunkK, ++it) {
+                for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
                     const uint32_t stage = it % a.nstages;
                     mbar_wait(&full_bar[stage], (it / a.nstages) & 1u);
                     tc_fence_after();
                     const uint32_t w_addr = smem_u32(smem + a.off_ring + stage * a.stage_bytes);
-                    const int ck = st.kp - k0 < kTcChunkK ? st.kp - k0 : kTcChunkK;
+                    const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
                     for (int kk = 0; kk < ck / 16; ++kk) {
                         const int q = k0 / 16 + kk;  // K16 step inside the A operand
                         const uint64_t ad = umma_smem_desc(a_addr + (uint32_t)q * 2u * lbo_a, lbo_a, 128);
@@ -211,7 +254,8 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                     umma_commit(&empty_bar[stage]);  // the stage is free once these MMAs have read it
                 }
                 if (st.epi) {
-                    umma_commit(&mma_bar);
+                    if (C > 1) umma_commit_multicast(&mma_bar, (uint16_t)((1u << C) - 1u));
+                    else umma_commit(&mma_bar);
                     ++need;
                 }
             }
@@ -296,18 +340,19 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
 
         const uint32_t taddr_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
         const int m = tid;  // this thread's row = its TMEM lane
-        uint32_t mma_phase = 0;
+        uint32_t mma_phase = 0, xev = 0;
         for (int s = 0; s < a.nsteps; ++s) {
             const TcStep& st = a.st[s];
             if (!st.epi) continue;
-            mbar_wait(&mma_bar, mma_phase & 1u);
+            mbar_wait(&mma_bar, mma_phase & 1u);  // all C CTAs have finished the MMAs up to this step
             ++mma_phase;
             tc_fence_after();
-            const float* sc = ss + st.ss_idx;
-            const float* sh = ss + a.total_ch + st.ss_idx;
+            const int slice0 = (int)rank * st.n;  // first channel of this CTA's N slice inside the step
+            const float* sc = ss + st.ss_idx + slice0;
+            const float* sh = ss + a.total_ch + st.ss_idx + slice0;
             const uint32_t taddr = taddr_lane + st.tmem_col;
             if (st.epi == 1) {
-                unsigned char* outp = smem + st.out_off;
+                unsigned char* outp = smem + st.out_off + (size_t)(slice0 >> 3) * kTcM * 16;  // this slice's K groups
                 for (int c0 = 0; c0 < st.n; c0 += 32) {
                     uint32_t r[2][16];
                     tmem_ld16_issue(taddr + (uint32_t)c0, r[0]);
@@ -336,6 +381,17 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                     }
                 }
                 fence_proxy_async();
+                if (C > 1) {
+                    // push the slice (contiguous: n / 8 K-groups x 128 rows x 16 B) into every peer's operand buffer
+                    epi_bar_sync();
+                    if (tid == 0) {
+                        const uint32_t src = smem_u32(outp), bytes = (uint32_t)st.n * (kTcM * 2u);
+                        const uint32_t bar = smem_u32(&x_bar[xev & 1u]);
+                        for (uint32_t q = 0; q < C; ++q)
+                            if (q != rank) bulk_copy_to_peer(mapa_shared(src, q), src, bytes, mapa_shared(bar, q));
+                    }
+                    ++xev;
+                }
             } else {
                 // ---- max over each group's K rows ----
                 const int row = row0 + m;
@@ -366,14 +422,14 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                         if ((size_t)(g0 + g) * a.K >= (size_t)a.rows) continue;
                         float v = pool[(g * wpg) * st.n + c];
                         for (int w = 1; w < wpg; ++w) v = fmaxf(v, pool[(g * wpg + w) * st.n + c]);
-                        a.out[(size_t)(g0 + g) * a.cout + st.out_c0 + c] = v;
+                        a.out[(size_t)(g0 + g) * a.cout + st.out_c0 + slice0 + c] = v;
                     }
                     epi_bar_sync();  // pool is reused by the next pooled step
                 } else {
                     const bool warp_uniform_group = (a.K % 32) == 0;
                     const int wrow = row0 + warp * 32;
                     const int g = (warp_uniform_group ? wrow : (valid ? row : 0)) / a.K;
-                    unsigned int* obase = reinterpret_cast<unsigned int*>(a.out) + (size_t)g * a.cout + st.out_c0;
+                    unsigned int* obase = reinterpret_cast<unsigned int*>(a.out) + (size_t)g * a.cout + st.out_c0 + slice0;
                     for (int c0 = 0; c0 < st.n; c0 += 16) {
                         uint32_t r[16];
                         tmem_ld16_issue(taddr + (uint32_t)c0, r);
@@ -401,6 +457,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
 
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();  // no CTA leaves while a peer may still push slices or commits into it
     if (warp == 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols)
                      : "memory");
@@ -409,12 +466,12 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
 
 // ---- host side: the step table, the shared-memory layout and the packed-blob layout ----------------
 struct TcBlock {
-    int layer, k0, klen, kp, n0, nlen;
-    uint32_t w_off;
+    int layer, k0, klen, kp, n0, nlen;  // logical block: W[n0 .. n0+nlen, k0 .. k0+klen], K padded to kp
+    uint32_t w_off, sub_bytes;          // blob offset of rank 0's sub-block; bytes between ranks' sub-blocks
 };
 struct TcPlan {
     bool ok;
-    int nsteps, nblocks, kp0, total_ch;
+    int nsteps, nblocks, kp0, total_ch, C;
     int n[3];
     TcStep st[kTcMaxSteps];
     TcBlock blk[kTcMaxBlocks];
@@ -422,9 +479,12 @@ struct TcPlan {
     size_t blob_bytes;
 };
 
-static TcPlan tc_plan(int D, const int* cout) {
+// C = CTAs per row tile (N split over a cluster): every step computes n / C channels per CTA.
+static TcPlan tc_plan(int D, const int* cout, int C) {
     TcPlan p = {};
     p.ok = false;
+    p.C = C;
+    if (C != 1 && C != 2 && C != 4 && C != 8) return p;
     const int n0 = cout[0], n1 = cout[1], n2 = cout[2];
     for (int l = 0; l < 3; ++l) {
         p.n[l] = cout[l];
@@ -433,36 +493,54 @@ static TcPlan tc_plan(int D, const int* cout) {
     if (n0 > kTcMaxN) return p;
     const int h1 = n1 > kTcMaxN ? 2 : 1, h2 = n2 > kTcMaxN ? 2 : 1;  // N halves of layers 1 and 2
     const int n1h = n1 / h1, n2h = n2 / h2;
+    if ((n0 % (16 * C)) || (n1h % (16 * C)) || (n2h % (16 * C))) return p;  // per-CTA slices: multiples of 16 columns
+    const int n0c = n0 / C, n1c = n1h / C, n2c = n2h / C;
     p.kp0 = (int)align_up((size_t)(3 + D), 16);
     p.total_ch = n0 + n1 + n2;
 
-    // weight blocks in the blob
+    // weight blocks in the blob: C consecutive sub-blocks [kp/8][nlen/C][8] per logical block
     uint32_t woff = 0;
-    auto add_block = [&](int layer, int k0, int klen, int kp, int nb0, int nlen) -> uint32_t {
-        TcBlock& b = p.blk[p.nblocks++];
+    auto add_block = [&](int layer, int k0, int klen, int kp, int nb0, int nlen) -> int {
+        TcBlock& b = p.blk[p.nblocks];
         b.layer = layer; b.k0 = k0; b.klen = klen; b.kp = kp; b.n0 = nb0; b.nlen = nlen; b.w_off = woff;
-        woff += (uint32_t)align_up((size_t)kp * nlen * 2, 128);
-        return b.w_off;
+        b.sub_bytes = (uint32_t)align_up((size_t)kp * (nlen / C) * 2, 128);
+        woff += b.sub_bytes * C;
+        return p.nblocks++;
     };
-    const uint32_t w0 = add_block(0, 0, 3 + D, p.kp0, 0, n0);
-    uint32_t w1[2] = {0, 0}, w2[2][2] = {{0, 0}, {0, 0}};
-    for (int kh = 0; kh < h1; ++kh) w1[kh] = add_block(1, 0, n0, n0, kh * n1h, n1h);
+    const int b0 = add_block(0, 0, 3 + D, p.kp0, 0, n0);
+    int b1[2] = {0, 0}, b2[2][2] = {{0, 0}, {0, 0}};
+    for (int kh = 0; kh < h1; ++kh) b1[kh] = add_block(1, 0, n0, n0, kh * n1h, n1h);
     for (int fh = 0; fh < h2; ++fh)
-        for (int kh = 0; kh < h1; ++kh) w2[kh][fh] = add_block(2, kh * n1h, n1h, n1h, fh * n2h, n2h);
+        for (int kh = 0; kh < h1; ++kh) b2[kh][fh] = add_block(2, kh * n1h, n1h, n1h, fh * n2h, n2h);
     p.ss_blob_off = woff;
     p.blob_bytes = (size_t)woff + (size_t)2 * p.total_ch * sizeof(float);
 
-    // shared memory
-    const int max_n = n0 > n1h ? (n0 > n2h ? n0 : n2h) : (n1h > n2h ? n1h : n2h);
-    p.stage_bytes = (uint32_t)max_n * kTcChunkK * 2;
+    // shared memory (operand buffers hold the FULL width: the peers' slices are pushed into them)
+    const int max_nc = n0c > n1c ? (n0c > n2c ? n0c : n2c) : (n1c > n2c ? n1c : n2c);
+    // K rows per chunk of a step: as many as fit a ring stage (narrow per-CTA slices get long chunks, so that the
+    // number of dependent TMA round trips stays small)
+    auto chunk_rows = [](int kp, int nc) {
+        int ck = kTcStageBytes / (nc * 2) / 16 * 16;
+        if (ck < 16) ck = 16;
+        return ck < kp ? ck : kp;
+    };
+    p.stage_bytes = 0;
+    {
+        const int kps[3] = {p.kp0, n0, n1h}, ncs[3] = {n0c, n1c, n2c};
+        for (int l = 0; l < 3; ++l) {
+            const uint32_t sb = (uint32_t)chunk_rows(kps[l], ncs[l]) * ncs[l] * 2;
+            if (sb > p.stage_bytes) p.stage_bytes = sb;
+        }
+        p.stage_bytes = (uint32_t)align_up(p.stage_bytes, 128);
+    }
     const uint32_t size_x = (uint32_t)kTcM * (p.kp0 > n1h ? p.kp0 : n1h) * 2;  // layer-0 input, later a layer-1 half
     const uint32_t size_h = (uint32_t)kTcM * n0 * 2;                             // layer-0 output
     const uint32_t size_ss = (uint32_t)align_up((size_t)2 * p.total_ch * sizeof(float), 128);
-    const uint32_t size_pool = (uint32_t)align_up((size_t)4 * n2h * sizeof(float), 128);
+    const uint32_t size_pool = (uint32_t)align_up((size_t)4 * n2c * sizeof(float), 128);
     const uint32_t fixed = size_x + size_h + size_ss + size_pool;
     const uint32_t limit = 225 * 1024;
-    int total_chunks = (p.kp0 + kTcChunkK - 1) / kTcChunkK;
-    total_chunks += h2 * h1 * ((n0 + kTcChunkK - 1) / kTcChunkK + (n1h + kTcChunkK - 1) / kTcChunkK);
+    auto nchunks = [&](int kp, int nc) { const int ck = chunk_rows(kp, nc); return (kp + ck - 1) / ck; };
+    int total_chunks = nchunks(p.kp0, n0c) + h2 * h1 * (nchunks(n0, n1c) + nchunks(n1h, n2c));
     p.nstages = kTcMaxStages;
     while (p.nstages > 2 && (fixed + p.nstages * p.stage_bytes > limit || (int)p.nstages > total_chunks)) --p.nstages;
     if (fixed + p.nstages * p.stage_bytes > limit) return p;
@@ -473,44 +551,61 @@ static TcPlan tc_plan(int D, const int* cout) {
     p.off_pool = p.off_ss + size_ss;
     p.smem_bytes = p.off_pool + size_pool;
 
-    // steps
+    // steps (n = per-CTA slice width; ss_idx / out_c0 = first channel of the whole step, the kernel adds rank * n)
     const bool split = h1 * h2 > 1;
-    auto add_step = [&](uint32_t a_off, uint32_t out_off, uint32_t w_off, int kp, int n, int col, int out_c0, int ss_idx,
+    const int l1col = split ? (int)align_up((size_t)(n0c > n2c ? n0c : n2c), 32) : 0;  // layer-1 accumulator next to layer 2's
+    auto add_step = [&](uint32_t a_off, uint32_t out_off, int blk, int kp, int n, int col, int out_c0, int ss_idx,
                         int acc, int epi) {
         TcStep& s = p.st[p.nsteps++];
-        s.a_off = a_off; s.out_off = out_off; s.w_off = w_off; s.kp = (uint16_t)kp; s.n = (uint16_t)n;
+        s.a_off = a_off; s.out_off = out_off; s.w_off = p.blk[blk].w_off; s.w_stride = p.blk[blk].sub_bytes;
+        s.kp = (uint16_t)kp; s.n = (uint16_t)n; s.ck = (uint16_t)chunk_rows(kp, n);
         s.tmem_col = (uint16_t)col; s.out_c0 = (uint16_t)out_c0; s.ss_idx = (uint16_t)ss_idx;
         s.acc = (uint8_t)acc; s.epi = (uint8_t)epi;
     };
-    add_step(off_x, off_h, w0, p.kp0, n0, 0, 0, 0, 0, 1);
+    add_step(off_x, off_h, b0, p.kp0, n0c, 0, 0, 0, 0, 1);
     for (int fh = 0; fh < h2; ++fh)
         for (int kh = 0; kh < h1; ++kh) {
-            add_step(off_h, off_x, w1[kh], n0, n1h, split ? kTcMaxN : 0, 0, n0 + kh * n1h, 0, 1);
-            add_step(off_x, 0, w2[kh][fh], n1h, n2h, 0, fh * n2h, n0 + n1 + fh * n2h, kh > 0, kh == h1 - 1 ? 2 : 0);
+            // the layer-1 half's output lands in buffer X at K offset 0 (it is the whole K range of the next step)
+            add_step(off_h, off_x, b1[kh], n0, n1c, l1col, 0, n0 + kh * n1h, 0, 1);
+            add_step(off_x, 0, b2[kh][fh], n1h, n2c, 0, fh * n2h, n0 + n1 + fh * n2h, kh > 0, kh == h1 - 1 ? 2 : 0);
         }
-    const int cols = split ? 2 * kTcMaxN : max_n;
+    const int cols = (split ? l1col + n1c : 0) > max_nc ? l1col + n1c : max_nc;
     p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     p.ok = true;
     return p;
 }
 
-bool sa_mlp_tc_supported(int D, const int* cout) { return tc_plan(D, cout).ok; }
-size_t sa_mlp_tc_blob_bytes(int D, const int* cout) { return tc_plan(D, cout).blob_bytes; }
+bool sa_mlp_tc_supported(int D, const int* cout) { return tc_plan(D, cout, 1).ok; }
 
-int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, void* blob, cudaStream_t stream) {
-    const TcPlan p = tc_plan(D, mlp->cout);
+// CTAs per row tile: split N over a cluster while the launch would otherwise leave most SMs idle.
+int sa_mlp_tc_pick_cluster(long tiles, int D, const int* cout) {
+    int best = 1;
+    for (int C = 2; C <= 8; C *= 2)
+        if (tiles * C <= kNumSMs && tc_plan(D, cout, C).ok) best = C;
+    return best;
+}
+size_t sa_mlp_tc_blob_bytes(int D, const int* cout, int C) {
+    const TcPlan p = tc_plan(D, cout, C);
+    return p.ok ? p.blob_bytes : 0;
+}
+
+int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, int C, void* blob, cudaStream_t stream) {
+    const TcPlan p = tc_plan(D, mlp->cout, C);
     if (!p.ok) {
-        set_error("sa_mlp pack (tensor-core path): unsupported layer widths");
+        set_error("sa_mlp pack (tensor-core path): unsupported layer widths / cluster size");
         return PCST_ERR_UNSUPPORTED;
     }
     const int cin[3] = {3 + D, p.n[0], p.n[1]};
     for (int i = 0; i < p.nblocks; ++i) {
         const TcBlock& b = p.blk[i];
-        const int total = b.kp * b.nlen;
-        tc_pack_block_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
-            mlp->w[b.layer], cin[b.layer], b.k0, b.klen, b.kp, b.n0, b.nlen, b.layer == 0 ? D : -1,
-            reinterpret_cast<__nv_bfloat16*>((char*)blob + b.w_off));
-        PCST_CUDA(cudaGetLastError());
+        const int nc = b.nlen / C;
+        const int total = b.kp * nc;
+        for (int r = 0; r < C; ++r) {
+            tc_pack_block_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
+                mlp->w[b.layer], cin[b.layer], b.k0, b.klen, b.kp, b.n0 + r * nc, nc, b.layer == 0 ? D : -1,
+                reinterpret_cast<__nv_bfloat16*>((char*)blob + b.w_off + (size_t)r * b.sub_bytes));
+            PCST_CUDA(cudaGetLastError());
+        }
     }
     float* ss = reinterpret_cast<float*>((char*)blob + p.ss_blob_off);
     int at = 0;
@@ -523,10 +618,10 @@ int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, void* blob, cudaStream_t strea
 }
 
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
-                  int K, int D, const int* cout, const void* blob, float* out, cudaStream_t stream) {
-    const TcPlan p = tc_plan(D, cout);
+                  int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream) {
+    const TcPlan p = tc_plan(D, cout, C);
     if (!p.ok) {
-        set_error("sa_mlp_max (tensor-core path): unsupported layer widths");
+        set_error("sa_mlp_max (tensor-core path): unsupported layer widths / cluster size");
         return PCST_ERR_UNSUPPORTED;
     }
     const size_t rows_sz = (size_t)B * S * K;
@@ -546,11 +641,24 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     a.off_ss = p.off_ss; a.off_pool = p.off_pool; a.tmem_cols = p.tmem_cols;
     a.out = out;
     a.pool_atomic = !(K == 32 || K == 64 || K == 128);
+    a.cluster = (uint32_t)C;
     if (a.pool_atomic) PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * cout[2] * sizeof(float), stream));
     PCST_CUDA(cudaFuncSetAttribute(sa_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    const int grid = (a.rows + kTcM - 1) / kTcM;
-    sa_mlp_tc_kernel<<<grid, kTcThreads, p.smem_bytes, stream>>>(a);
-    return check_cuda(cudaGetLastError(), "sa_mlp_tc_kernel");
+    const int tiles = (a.rows + kTcM - 1) / kTcM;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles * C);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PCST_CUDA(cudaLaunchKernelEx(&cfg, sa_mlp_tc_kernel, a));
+    return PCST_OK;
 }
 
 }  // namespace pcst

@@ -118,15 +118,19 @@ class SetAbstraction(nn.Module):
             self._packed = {}
         return self._fold
 
-    def _packed_params(self):
-        """The folded parameters in the layout the kernels read, packed once per parameter version and
-        precision (bf16 UMMA operand blocks for the tensor-core path) -> (uint8 blob, padded Couts)."""
+    def _packed_params(self, B: int, S: int, K: int):
+        """The folded parameters in the layout the kernels read, packed once per parameter version, precision and
+        cluster split (bf16 UMMA operand blocks for the tensor-core path; stages with few rows split every layer's
+        channels over a thread-block cluster) -> (uint8 blob, padded Couts, cluster)."""
         ws, scs, shs = self._folded()
         prec = int(self.mlp_precision)
-        if prec not in self._packed:
-            D = ws[0].shape[1] - 3
-            self._packed[prec] = (ops.sa_mlp_pack(ws, scs, shs, D, prec), [int(w.shape[0]) for w in ws])
-        return self._packed[prec]
+        couts = [int(w.shape[0]) for w in ws]
+        D = ws[0].shape[1] - 3
+        cluster = ops.sa_mlp_pick_cluster(B, S, K, D, couts, prec)
+        key = (prec, cluster)
+        if key not in self._packed:
+            self._packed[key] = ops.sa_mlp_pack(ws, scs, shs, D, prec, cluster)
+        return self._packed[key], couts, cluster
 
     def _fused_ok(self, *tensors) -> bool:
         if self.training or len(self.mlp_convs) != 3:
@@ -148,8 +152,8 @@ class SetAbstraction(nn.Module):
         if self.group_all:
             new_xyz = torch.zeros(B, 1, 3, device=xyz.device)  # :82
             if fused:
-                packed, couts = self._packed_params()
-                new_points = ops.sa_mlp_max(xyz, points, None, None, packed, couts, self.mlp_precision)  # [B,1,C]
+                packed, couts, cluster = self._packed_params(B, 1, N)
+                new_points = ops.sa_mlp_max(xyz, points, None, None, packed, couts, self.mlp_precision, cluster)  # [B,1,C]
                 return new_xyz, new_points[:, 0, :cout]
             if points is not None:
                 grouped_points = torch.cat([xyz.view(B, 1, N, 3), points.view(B, 1, N, -1)], dim=-1)
@@ -176,8 +180,9 @@ class SetAbstraction(nn.Module):
     def _mlp_fused(self, xyz, points, new_xyz, group_idx) -> torch.Tensor:
         """Grouping gather + folded MLP + max-pool in one op -> [B,C_out,S] (a channel-first VIEW of the
         kernel's point-major output, so the caller's permute back, :128-129, is free)."""
-        packed, couts = self._packed_params()
-        out = ops.sa_mlp_max(xyz, points, new_xyz, group_idx, packed, couts, self.mlp_precision)  # [B,S,C]
+        B, S, K = group_idx.shape
+        packed, couts, cluster = self._packed_params(B, S, K)
+        out = ops.sa_mlp_max(xyz, points, new_xyz, group_idx, packed, couts, self.mlp_precision, cluster)  # [B,S,C]
         return out[:, :, :self.mlp_convs[-1].out_channels].permute(0, 2, 1)
 
     def apply_mlp(self, points):
@@ -185,11 +190,11 @@ class SetAbstraction(nn.Module):
         if self._fused_ok(points) and points.is_cuda:
             # a pre-grouped tensor: run it as B*S clouds of K points, one group each (group_all form)
             B, S, K, C = points.shape
-            packed, couts = self._packed_params()
+            packed, couts, cluster = self._packed_params(B * S, 1, K)
             flat = points.reshape(B * S, K, C)
             xyz = flat[..., :3].contiguous()
             feats = flat[..., 3:].contiguous() if C > 3 else None
-            out = ops.sa_mlp_max(xyz, feats, None, None, packed, couts, self.mlp_precision)  # [B*S,1,C]
+            out = ops.sa_mlp_max(xyz, feats, None, None, packed, couts, self.mlp_precision, cluster)  # [B*S,1,C]
             return out[:, 0, :self.mlp_convs[-1].out_channels].reshape(B, S, -1).permute(0, 2, 1)
         points = points.permute(0, 3, 1, 2)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
@@ -223,7 +228,9 @@ class PointNet2Encoder(nn.Module):
         side = _SIDE_STREAMS.get(dev)
         if side is None:
             side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
-        packs = [sa._packed_params()[0] for sa in (self.sa1, self.sa2, self.sa3)]
+        packs = [self.sa1._packed_params(B, self.sa1.npoint, self.sa1.nsample)[0],
+                 self.sa2._packed_params(B, self.sa2.npoint, self.sa2.nsample)[0],
+                 self.sa3._packed_params(B, 1, self.sa2.npoint)[0]]
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for blob in packs:  # 1.3 MB of packed weights -> L2 while the first FPS occupies 16 of the 148 SMs

@@ -270,9 +270,11 @@ def _cout3(couts: List[int]):
 
 
 @torch.library.custom_op("pcst::sa_mlp_pack", mutates_args=(), device_types="cuda")
-def sa_mlp_pack(weights: List[Tensor], scales: List[Tensor], shifts: List[Tensor], D: int, precision: int) -> Tensor:
+def sa_mlp_pack(weights: List[Tensor], scales: List[Tensor], shifts: List[Tensor], D: int, precision: int,
+                cluster: int) -> Tensor:
     """Pack the folded parameters of a 3-layer shared MLP once (bf16 UMMA operand blocks for the tensor-core
-    path, a plain fp32 blob otherwise) -> uint8 tensor, reused by every ``sa_mlp_max`` call."""
+    path, split into ``cluster`` N slices; a plain fp32 blob otherwise) -> uint8 tensor, reused by every
+    ``sa_mlp_max`` call with the same (precision, cluster)."""
     lib = _lib.load()
     _need_cuda(*weights, *scales, *shifts)
     if len(weights) != 3 or len(scales) != 3 or len(shifts) != 3:
@@ -289,27 +291,32 @@ def sa_mlp_pack(weights: List[Tensor], scales: List[Tensor], shifts: List[Tensor
         m.cout[l] = cin = weights[l].shape[0]
     dev = weights[0].device
     with torch.cuda.device(dev):
-        nb = lib.pcst_sa_mlp_packed_bytes(D, m.cout, precision)
+        nb = lib.pcst_sa_mlp_packed_bytes(D, m.cout, precision, cluster)
         if nb == 0:
-            raise ValueError("sa_mlp_pack: unsupported layer widths (Cout must be a multiple of 32, <= 1024)")
+            raise ValueError("sa_mlp_pack: unsupported layer widths (Cout must be a multiple of 32, <= 1024) or cluster size")
         packed = torch.empty(nb, dtype=torch.uint8, device=dev)
-        _call("pcst_sa_mlp_pack_f32", ctypes.byref(m), D, precision, _p(packed), nb, _stream())
+        _call("pcst_sa_mlp_pack_f32", ctypes.byref(m), D, precision, cluster, _p(packed), nb, _stream())
     return packed
 
 
 @sa_mlp_pack.register_fake
-def _(weights, scales, shifts, D, precision):
+def _(weights, scales, shifts, D, precision, cluster):
     return weights[0].new_empty(1, dtype=torch.uint8)
+
+
+def sa_mlp_pick_cluster(B: int, S: int, K: int, D: int, couts: List[int], precision: int) -> int:
+    """CTAs per 128-row tile the tensor-core kernel should use for this shape (1 on the fp32 path)."""
+    return int(_lib.load().pcst_sa_mlp_pick_cluster(B, S, K, D, _cout3(couts), precision))
 
 
 @torch.library.custom_op("pcst::sa_mlp_max", mutates_args=(), device_types="cuda")
 def sa_mlp_max(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], idx: Optional[Tensor],
-               packed: Tensor, couts: List[int], precision: int) -> Tensor:
+               packed: Tensor, couts: List[int], precision: int, cluster: int) -> Tensor:
     """Fused grouping gather + 3 x relu(scale * (W x) + shift) + max over each group -> [B,S,Cout] (POINT-major;
     the reference's channel-first layout is ``.permute(0, 2, 1)``).
 
     ``idx is None`` = group_all (one group holding the whole cloud, no centroid subtraction);
-    ``packed`` comes from ``sa_mlp_pack`` with the same ``couts`` / ``precision`` / D."""
+    ``packed`` comes from ``sa_mlp_pack`` with the same ``couts`` / ``precision`` / ``cluster`` / D."""
     lib = _lib.load()
     _need_cuda(xyz, feats, new_xyz, idx, packed)
     xyz = _f32c(xyz)
@@ -325,17 +332,17 @@ def sa_mlp_max(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], 
     c3 = _cout3(couts)
     out = torch.empty(B, S, int(couts[2]), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
-        if packed.numel() < lib.pcst_sa_mlp_packed_bytes(D, c3, precision):
-            raise ValueError("sa_mlp_max: `packed` does not match (D, couts, precision)")
+        if packed.numel() < lib.pcst_sa_mlp_packed_bytes(D, c3, precision, cluster):
+            raise ValueError("sa_mlp_max: `packed` does not match (D, couts, precision, cluster)")
         nb = lib.pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, c3, precision)
         ws = _workspace(nb, xyz.device)
-        _call("pcst_sa_mlp_max_f32", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, c3, precision,
+        _call("pcst_sa_mlp_max_f32", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, c3, precision, cluster,
               _p(packed), _p(out), _p(ws), ws.numel(), _stream(), kernels=1 if nb == 0 else 3)
     return out
 
 
 @sa_mlp_max.register_fake
-def _(xyz, feats, new_xyz, idx, packed, couts, precision):
+def _(xyz, feats, new_xyz, idx, packed, couts, precision, cluster):
     S = 1 if idx is None else idx.shape[1]
     return xyz.new_empty(xyz.shape[0], S, couts[2], dtype=torch.float32)
 

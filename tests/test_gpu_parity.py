@@ -297,6 +297,35 @@ def test_encoder_feature_dims_and_batches_against_oracle(api, dev, oracle, preci
     np.testing.assert_allclose(feat.cpu().numpy(), ref["feature"], rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("mlp,D,K", [([256, 512, 256], 256, 128), ([128, 128, 256], 128, 64), ([256, 512, 512], 29, 128)])
+def test_sa_mlp_tensor_core_every_cluster_split(api, dev, oracle, cluster, mlp, D, K):
+    """N split of every layer over a thread-block cluster of 1/2/4/8 CTAs (activation slices exchanged through
+    distributed shared memory): each split must reproduce the oracle within the bf16 tolerance and agree with
+    the unsplit kernel to the last bit (same MMAs per output element, only their placement changes)."""
+    torch.manual_seed(3)
+    sa = api.enc.SetAbstraction(None, None, None, in_channel=D, mlp=mlp, group_all=True).eval().to(dev)
+    sa.mlp_precision = 1
+    g = torch.Generator().manual_seed(5)
+    for bn in sa.mlp_bns:
+        bn.running_mean.copy_(torch.randn(bn.num_features, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(bn.num_features, generator=g) * 0.5 + 0.75)
+    B = 3
+    xyz = S.uniform_cloud(41, B, K)
+    feats = torch.randn(B, K, D, generator=torch.Generator().manual_seed(6))
+    ws, scs, shs = sa._folded()
+    couts = [int(w.shape[0]) for w in ws]
+    outs = {}
+    for c in (1, cluster):
+        packed = api.ops.sa_mlp_pack(ws, scs, shs, D, 1, c)
+        outs[c] = api.ops.sa_mlp_max(xyz.to(dev), feats.to(dev), None, None, packed, couts, 1, c)[:, 0, :mlp[2]]
+    assert torch.equal(outs[1], outs[cluster])
+    sd = {k: v.detach().cpu().numpy() for k, v in sa.state_dict().items()}
+    pts = torch.cat([xyz, feats], -1)[:, None]  # [B,1,K,3+D]
+    ref = oracle.apply_mlp(pts.numpy(), oracle.layers_from_state_dict(sd, ""))[:, :, 0]
+    np.testing.assert_allclose(outs[cluster].cpu().numpy(), ref, rtol=2e-2, atol=2e-2)
+
+
 def test_sa_mlp_tensor_core_ragged_groups(api, dev, oracle):
     """K not a multiple of 32 and a partial last row tile exercise the per-element pooling path."""
     torch.manual_seed(0)
