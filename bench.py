@@ -331,8 +331,11 @@ def main():
             "gpu_launches": launches_per_step * K * 2,
             "roofline": {"kernel": "fps_kernel<16> (SA1 farthest point sampling, 16-CTA cluster)", "bound": "hbm",
                          "achieved": fps_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fps_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": fps_ms_max,
-                         "model": "streaming-model bytes npoint*N*20 B per launch; the kernel keeps the cloud on chip"},
+                         "traffic": 1.46e6, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per "
+                         "launch (profiles/r01_ncu_full_kernels.md); = the cloud read once, the kernel keeps it on chip",
+                         "peak_source": peak_src, "kernel_ms": fps_ms_max,
+                         "model": "streaming-model bytes npoint*N*20 B per launch (SURVEY.md 8(d)): what an FPS that re-reads xyz and "
+                                  "running distances every iteration moves; the kernel is bound by its 512 serial cluster exchanges"},
             "op_ms_eager": op_ms,
             "chamfer": {"metric": "Chamfer NN pairs/sec (120k x 120k, both directions)", "value": world * pairs / (t_ch * 1e-3),
                         "unit": "pairs/s", "ms_per_call": t_ch,
