@@ -163,6 +163,14 @@ size_t pcst_nn_min_pair_workspace_bytes(int B, int N, int M);
 int pcst_nn_min_pair_f32(const float* a, const float* b, int B, int N, int M, int form, float* rowmin,
                          float* colmin, void* ws, size_t ws_bytes, pcst_stream_t stream);
 
+/* The same single sweep (loss form) WITH both argmins, for the backward of the Chamfer loss:
+ * rowarg [B,N] = lowest j attaining rowmin, colarg [B,M] = lowest i attaining colmin -- identical to the outputs of
+ * pcst_nn_min_f32(a, b, ..., rowarg) and pcst_nn_min_f32(b, a, ..., rowarg).  The sweep remembers only which
+ * 32-candidate / 256-row block held each minimum; two small fix-up kernels recover the exact first index. */
+size_t pcst_nn_min_pair_arg_workspace_bytes(int B, int N, int M);
+int pcst_nn_min_pair_arg_f32(const float* a, const float* b, int B, int N, int M, float* rowmin, int64_t* rowarg,
+                             float* colmin, int64_t* colarg, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
 /* Backward of chamfer_distance_chunked_optimized (autograd of models/losses.py:24-61).
  * pred [B,N,3], target [B,M,3]; arg_pt [B,N] / arg_tp [B,M] = the argmins returned by pcst_nn_min_f32
  * (form 0) for pred->target / target->pred; grad_out [B] = dL/d(chamfer[b]).

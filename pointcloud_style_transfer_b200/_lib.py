@@ -60,6 +60,9 @@ SIGNATURES = {
     "pcst_nn_min_pair_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_nn_min_pair_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    "pcst_nn_min_pair_arg_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcst_nn_min_pair_arg_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_size_t, c_void_p]),
     "pcst_chamfer_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                      c_void_p, c_void_p]),
     "pcst_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

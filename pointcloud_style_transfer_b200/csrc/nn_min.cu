@@ -306,6 +306,204 @@ nn_min_pair_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, 
     }
 }
 
+
+// ---- both directions in one sweep, WITH the argmins the Chamfer backward needs -------------------------------
+// Tracking an index per pair costs two extra ALU-pipe instructions per pair (the one-directional argmin kernel is
+// ALU-bound at half the speed of the value-only kernel).  Here the sweep only remembers, per row, WHICH 32-candidate
+// sub-block produced the minimum (one compare + two selects per row per 32 pairs) and, per candidate, which
+// 256-row block of the grid did (the warp that wins the REDUX / strip merge); both are merged across CTAs as 64-bit
+// (value bits << 32 | block) keys with atomicMin, so ties go to the lowest block.  Two small fix-up kernels then
+// re-evaluate the 32 (resp. 256) pairs of the winning block with the same arithmetic and return the FIRST index
+// whose clamped distance equals the minimum -- the reference's tie-break (torch.min returns the first minimum).
+// Rows are laid out so that a warp owns 256 CONSECUTIVE rows (thread t holds rows 8t .. 8t+7 of the CTA's 2048).
+__global__ void __launch_bounds__(kNNThreads, 2)
+nn_min_pair_arg_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N, int M, int Npad, int Mpad,
+                       int tiles_per_split, unsigned long long* __restrict__ rowkey,
+                       unsigned long long* __restrict__ colkey) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);                                         // [stages][1024]
+    unsigned int* colw = reinterpret_cast<unsigned int*>(smem_raw + kPairStages * kTileBytes);   // [2][8 warps][1024]
+    __shared__ __align__(8) uint64_t full_bar[kPairStages];
+    constexpr int R = kPairR;
+    constexpr int kWarps = kNNThreads / 32;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int total_tiles = Mpad / kTilePoints;
+    const int tile0 = blockIdx.y * tiles_per_split;
+    int ntiles = total_tiles - tile0;
+    if (ntiles > tiles_per_split) ntiles = tiles_per_split;
+    if (ntiles <= 0) return;  // uniform per CTA
+    const float4* cand = Bp + (size_t)b * Mpad + (size_t)tile0 * kTilePoints;
+
+    if (tid == 0) {
+        for (int s = 0; s < kPairStages; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int pre = ntiles < kPairStages ? ntiles : kPairStages;
+        for (int s = 0; s < pre; ++s) {
+            mbar_arrive_expect_tx(&full_bar[s], kTileBytes);
+            tma_load_1d(tiles + (size_t)s * kTilePoints, cand + (size_t)s * kTilePoints, kTileBytes, &full_bar[s]);
+        }
+    }
+
+    const int row0 = blockIdx.x * (kNNThreads * R) + tid * R;  // 8 consecutive rows per thread
+    const float4* arow = A + (size_t)b * Npad + row0;
+    float2 vx[R / 2], vy[R / 2], vz[R / 2], vn[R / 2];
+    float best[R];
+    int bblk[R];
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+        const float4 p = arow[r], q = arow[r + 1];
+        vx[r / 2] = make_float2(p.x, q.x);
+        vy[r / 2] = make_float2(p.y, q.y);
+        vz[r / 2] = make_float2(p.z, q.z);
+        vn[r / 2] = make_float2(p.w, q.w);
+        best[r] = best[r + 1] = __int_as_float(0x7f800000);
+        bblk[r] = bblk[r + 1] = 0;
+    }
+
+    auto pair8 = [&](const float4& c, float (&d)[R]) {
+        const float2 cx = make_float2(c.x, c.x), cy = make_float2(c.y, c.y), cz = make_float2(c.z, c.z),
+                     cw = make_float2(c.w, c.w);
+#pragma unroll
+        for (int h = 0; h < R / 2; ++h) {
+            const float2 dot = __ffma2_rn(vz[h], cz, __ffma2_rn(vy[h], cy, __fmul2_rn(vx[h], cx)));
+            const float2 o = __ffma2_rn(make_float2(-2.0f, -2.0f), dot, __fadd2_rn(vn[h], cw));  // losses.py:38
+            d[2 * h] = o.x;
+            d[2 * h + 1] = o.y;
+        }
+    };
+    auto colmin8 = [&](const float (&d)[R]) -> unsigned int {
+        float m = fmin3(fmin3(d[0], d[1], d[2]), fmin3(d[3], d[4], d[5]), fminf(d[6], d[7]));
+        m = fmaxf(m, 0.0f);
+        return __reduce_min_sync(0xffffffffu, __float_as_uint(m));
+    };
+
+    const unsigned int my_block = blockIdx.x * kWarps + warp;  // this warp's 256-row block of the grid
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kPairStages;
+        mbar_wait(&full_bar[s], (uint32_t)((t / kPairStages) & 1));
+        const float4* tile = tiles + (size_t)s * kTilePoints;
+        unsigned int* strip = colw + ((size_t)(t & 1) * kWarps + warp) * kTilePoints;
+#pragma unroll 1
+        for (int jb = 0; jb < kTilePoints; jb += 32) {
+            unsigned int mine = 0x7f800000u;
+            float sub[R];  // minimum of this 32-candidate sub-block per row
+#pragma unroll
+            for (int r = 0; r < R; ++r) sub[r] = __int_as_float(0x7f800000);
+#pragma unroll 4
+            for (int jj = 0; jj < 32; jj += 2) {
+                float d0[R], d1[R];
+                pair8(tile[jb + jj], d0);
+                pair8(tile[jb + jj + 1], d1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) sub[r] = fmin3(sub[r], d0[r], d1[r]);
+                const unsigned int u0 = colmin8(d0), u1 = colmin8(d1);
+                if (lane == jj) mine = u0;
+                if (lane == jj + 1) mine = u1;
+            }
+            const int blk = (tile0 + t) * (kTilePoints / 32) + (jb >> 5);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float m = fmaxf(sub[r], 0.0f);  // clamp, then strict <: ties keep the earlier sub-block
+                if (m < best[r]) {
+                    best[r] = m;
+                    bblk[r] = blk;
+                }
+            }
+            strip[jb + lane] = mine;
+        }
+        __syncthreads();
+        if (tid == 0 && t + kPairStages < ntiles) {
+            mbar_arrive_expect_tx(&full_bar[s], kTileBytes);
+            tma_load_1d(tiles + (size_t)s * kTilePoints, cand + (size_t)(t + kPairStages) * kTilePoints, kTileBytes,
+                        &full_bar[s]);
+        }
+        const unsigned int* base = colw + (size_t)(t & 1) * kWarps * kTilePoints;
+        const int jbase = (tile0 + t) * kTilePoints;
+        for (int q = tid; q < kTilePoints; q += kNNThreads) {
+            unsigned int v = base[q], w = 0;
+#pragma unroll
+            for (int x = 1; x < kWarps; ++x) {
+                const unsigned int u = base[x * kTilePoints + q];
+                if (u < v) {  // strict: the lowest warp (= lowest rows) wins a tie
+                    v = u;
+                    w = x;
+                }
+            }
+            if (jbase + q < M)
+                atomicMin(colkey + (size_t)b * M + jbase + q,
+                          ((unsigned long long)v << 32) | (unsigned long long)(blockIdx.x * kWarps + w));
+        }
+    }
+    (void)my_block;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = row0 + r;
+        if (i < N)
+            atomicMin(rowkey + (size_t)b * N + i,
+                      ((unsigned long long)__float_as_uint(best[r]) << 32) | (unsigned long long)(unsigned int)bblk[r]);
+    }
+}
+
+__global__ void nn_min_key_init_kernel(unsigned long long* a, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = ~0ull;
+}
+
+__device__ __forceinline__ float pair_loss_clamped(const float4& a, const float4& c) {
+    return fmaxf(__fmaf_rn(-2.0f, dot3_chain(a.x, a.y, a.z, c.x, c.y, c.z), __fadd_rn(a.w, c.w)), 0.0f);
+}
+
+// rows: one thread per row re-evaluates the 32 candidates of the winning sub-block
+__global__ void nn_min_pair_fix_rows_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N, int M,
+                                            int Npad, int Mpad, const unsigned long long* __restrict__ rowkey,
+                                            float* __restrict__ rowmin, int64_t* __restrict__ rowarg) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned long long key = rowkey[(size_t)b * N + i];
+    const float best = __uint_as_float((unsigned int)(key >> 32));
+    const int j0 = (int)(unsigned int)(key & 0xffffffffull) * 32;
+    const float4 a = A[(size_t)b * Npad + i];
+    const float4* c = Bp + (size_t)b * Mpad + j0;
+    int arg = j0;
+#pragma unroll 4
+    for (int j = 31; j >= 0; --j)
+        if (pair_loss_clamped(a, c[j]) == best) arg = j0 + j;  // descending: the lowest matching index survives
+    rowmin[(size_t)b * N + i] = best;
+    rowarg[(size_t)b * N + i] = arg;
+}
+
+// columns: one warp per candidate re-evaluates the 256 rows of the winning block
+__global__ void nn_min_pair_fix_cols_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N, int M,
+                                            int Npad, int Mpad, const unsigned long long* __restrict__ colkey,
+                                            float* __restrict__ colmin, int64_t* __restrict__ colarg) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= M) return;  // whole warp
+    const unsigned long long key = colkey[(size_t)b * M + j];
+    const float best = __uint_as_float((unsigned int)(key >> 32));
+    const int i0 = (int)(unsigned int)(key & 0xffffffffull) * 256;
+    const float4 c = Bp[(size_t)b * Mpad + j];
+    const float4* a = A + (size_t)b * Npad + i0;
+    unsigned int arg = 0xffffffffu;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        const int i = k * 32 + lane;
+        if (pair_loss_clamped(a[i], c) == best) arg = (unsigned int)(i0 + i);
+    }
+    arg = __reduce_min_sync(0xffffffffu, arg);
+    if (lane == 0) {
+        colmin[(size_t)b * M + j] = best;
+        colarg[(size_t)b * M + j] = (int64_t)arg;
+    }
+}
+
 __global__ void nn_min_pair_init_kernel(unsigned int* a, size_t na, unsigned int* b, size_t nb) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < na) a[i] = 0x7f800000u;
@@ -490,6 +688,48 @@ extern "C" int pcst_nn_min_pair_f32(const float* a, const float* b, int B, int N
         PCST_CUDA(cudaGetLastError());
     }
     return PCST_OK;
+}
+
+
+extern "C" size_t pcst_nn_min_pair_arg_workspace_bytes(int B, int N, int M) {
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    const NNPlan p = make_plan(B, N, M, kPairR);
+    return p.off_key + align_up((size_t)B * N * 8, 256) + align_up((size_t)B * M * 8, 256);
+}
+
+extern "C" int pcst_nn_min_pair_arg_f32(const float* a, const float* b, int B, int N, int M, float* rowmin,
+                                        int64_t* rowarg, float* colmin, int64_t* colarg, void* ws, size_t ws_bytes,
+                                        pcst_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCST_CHECK_ARG(a && b && rowmin && rowarg && colmin && colarg, "null pointer");
+    PCST_CHECK_ARG(B > 0 && N > 0 && M > 0, "B, N, M must be positive");
+    PCST_CHECK_ARG(B <= 65535, "B must be <= 65535");
+    const NNPlan p = make_plan(B, N, M, kPairR);
+    const size_t need = pcst_nn_min_pair_arg_workspace_bytes(B, N, M);
+    if (!ws || ws_bytes < need || ((uintptr_t)ws & 255)) {
+        set_error("pcst_nn_min_pair_arg_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need);
+        return PCST_ERR_WORKSPACE;
+    }
+    char* w = (char*)ws;
+    float4* A = (float4*)(w + p.off_a);
+    float4* Bp = (float4*)(w + p.off_b);
+    unsigned long long* rowkey = (unsigned long long*)(w + p.off_key);
+    unsigned long long* colkey = (unsigned long long*)(w + p.off_key + align_up((size_t)B * N * 8, 256));
+    int st;
+    if ((st = launch_pack(a, B, N, p.Npad, A, stream)) != PCST_OK) return st;
+    if ((st = launch_pack(b, B, M, p.Mpad, Bp, stream)) != PCST_OK) return st;
+    const size_t nkeys = ((char*)colkey - (char*)rowkey) / 8 + (size_t)B * M;  // both key arrays and the padding between
+    nn_min_key_init_kernel<<<(unsigned)((nkeys + 255) / 256), 256, 0, stream>>>(rowkey, nkeys);
+    PCST_CUDA(cudaGetLastError());
+    const int smem = kPairStages * kTileBytes + 2 * (kNNThreads / 32) * kTilePoints * (int)sizeof(unsigned int);
+    PCST_CUDA(cudaFuncSetAttribute(nn_min_pair_arg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(p.row_tiles, p.splits, B);
+    nn_min_pair_arg_kernel<<<grid, kNNThreads, smem, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, p.tiles_per_split, rowkey, colkey);
+    PCST_CUDA(cudaGetLastError());
+    nn_min_pair_fix_rows_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, rowkey, rowmin, rowarg);
+    PCST_CUDA(cudaGetLastError());
+    nn_min_pair_fix_cols_kernel<<<dim3((M + 7) / 8, B), 256, 0, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, colkey, colmin, colarg);
+    return check_cuda(cudaGetLastError(), "nn_min_pair_fix_cols_kernel");
 }
 
 // ---- backward of the Chamfer loss (models/losses.py:24-61 under autograd) ---------------------

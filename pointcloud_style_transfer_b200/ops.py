@@ -52,7 +52,7 @@ def _workspace(nbytes: int, device) -> Tensor:
 # roofline's live kernel durations).  KERNELS_PER_CALL counts __global__ launches (memsets excluded).
 KERNELS_PER_CALL = {"pcst_l2_prefetch": 1, "pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
-                    "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 7, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
+                    "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 7, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_nn_min_pair_arg_f32": 6, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
                     "pcst_knn_interpolate_f32": 1}
 launch_count = 0
 _event_log = None  # None = off; else list of (name, start_event, end_event)
@@ -398,6 +398,33 @@ def _(a, b, form):
             a.new_empty(b.shape[0], b.shape[1], dtype=torch.float32))
 
 
+@torch.library.custom_op("pcst::nn_min_pair_arg", mutates_args=(), device_types="cuda")
+def nn_min_pair_arg(a: Tensor, b: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Loss-form row / column minima AND their argmins from one sweep -> (rowmin [B,N], rowarg [B,N] int64,
+    colmin [B,M], colarg [B,M] int64); ties go to the lowest index like ``torch.min``."""
+    lib = _lib.load()
+    _need_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    rowmin = torch.empty(B, N, dtype=torch.float32, device=a.device)
+    colmin = torch.empty(B, M, dtype=torch.float32, device=a.device)
+    rowarg = torch.empty(B, N, dtype=torch.int64, device=a.device)
+    colarg = torch.empty(B, M, dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        ws = _workspace(lib.pcst_nn_min_pair_arg_workspace_bytes(B, N, M), a.device)
+        _call("pcst_nn_min_pair_arg_f32", _p(a), _p(b), B, N, M, _p(rowmin), _p(rowarg), _p(colmin), _p(colarg), _p(ws),
+              ws.numel(), _stream())
+    return rowmin, rowarg, colmin, colarg
+
+
+@nn_min_pair_arg.register_fake
+def _(a, b):
+    B, N, M = a.shape[0], a.shape[1], b.shape[1]
+    return (a.new_empty(B, N, dtype=torch.float32), a.new_empty(B, N, dtype=torch.int64),
+            a.new_empty(B, M, dtype=torch.float32), a.new_empty(B, M, dtype=torch.int64))
+
+
 @torch.library.custom_op("pcst::chamfer_bwd", mutates_args=(), device_types="cuda")
 def chamfer_bwd(pred: Tensor, target: Tensor, arg_pt: Tensor, arg_tp: Tensor, grad_out: Tensor) -> Tuple[Tensor, Tensor]:
     lib = _lib.load()
@@ -424,9 +451,8 @@ class _ChamferLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
         need_grad = pred.requires_grad or target.requires_grad
-        if need_grad:  # the backward needs both argmins: two one-directional sweeps with index tracking
-            d1, a1 = nn_min(pred, target, 0, True)
-            d2, a2 = nn_min(target, pred, 0, True)
+        if need_grad:  # the backward needs both argmins: still one sweep (block tracking + exact fix-up)
+            d1, a1, d2, a2 = nn_min_pair_arg(pred, target)
             ctx.save_for_backward(pred, target, a1, a2)
         else:          # values only: one sweep serves both directions
             d1, d2 = nn_min_pair(pred, target, 0)

@@ -501,6 +501,37 @@ def test_nn_min_pair_golden_lattice_and_120k_equals_two_sweeps(api, dev, golden)
     assert torch.equal(c, api.ops.nn_min(b, a, 2, False)[0])
 
 
+@pytest.mark.parametrize("B,N,M", [(2, 4096, 3900), (1, 1, 5), (1, 5, 1), (3, 1025, 1023), (2, 2049, 7777), (1, 30000, 30000)])
+def test_nn_min_pair_arg_matches_oracle_both_directions(api, dev, oracle, B, N, M):
+    """One sweep that also returns both argmins (block tracking + exact fix-up): values and FIRST-minimum indices
+    bit-equal to the oracle's two one-directional evaluations."""
+    a, b = S.uniform_cloud(12, B, N).numpy(), S.uniform_cloud(22, B, M).numpy()
+    r, ra, c, ca = api.ops.nn_min_pair_arg(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
+    ref_r, ref_ra = oracle.nn_min(a, b, 0, want_arg=True)
+    ref_c, ref_ca = oracle.nn_min(b, a, 0, want_arg=True)
+    assert np.array_equal(bits(r.cpu().numpy()), bits(ref_r)) and np.array_equal(ra.cpu().numpy(), ref_ra)
+    assert np.array_equal(bits(c.cpu().numpy()), bits(ref_c)) and np.array_equal(ca.cpu().numpy(), ref_ca)
+
+
+def test_nn_min_pair_arg_ties_duplicates_and_120k(api, dev, oracle, golden):
+    # exact ties everywhere: a lattice cloud against itself with every point duplicated (argmin = first duplicate)
+    g = golden("lattice")
+    x = torch.from_numpy(np.concatenate([g["x"], g["x"]], axis=1)).to(dev)
+    y = torch.from_numpy(g["y"]).to(dev)
+    for a, b in ((x, x), (x, y), (y, x)):
+        r, ra, c, ca = api.ops.nn_min_pair_arg(a, b)
+        ref_r, ref_ra = oracle.nn_min(a.cpu().numpy(), b.cpu().numpy(), 0, want_arg=True)
+        ref_c, ref_ca = oracle.nn_min(b.cpu().numpy(), a.cpu().numpy(), 0, want_arg=True)
+        assert np.array_equal(bits(r.cpu().numpy()), bits(ref_r)) and np.array_equal(ra.cpu().numpy(), ref_ra)
+        assert np.array_equal(bits(c.cpu().numpy()), bits(ref_c)) and np.array_equal(ca.cpu().numpy(), ref_ca)
+    # full size against the one-directional argmin kernel (itself oracle-checked on a row subset above)
+    p, t = S.lidar_scan(0).to(dev), S.lidar_scan(1).to(dev)
+    r, ra, c, ca = api.ops.nn_min_pair_arg(p, t)
+    d1, a1 = api.ops.nn_min(p, t, 0, True)
+    d2, a2 = api.ops.nn_min(t, p, 0, True)
+    assert torch.equal(r, d1) and torch.equal(ra, a1) and torch.equal(c, d2) and torch.equal(ca, a2)
+
+
 def test_nn_min_lattice_order_independent(api, dev, golden):
     g = golden("lattice")
     x, y = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)

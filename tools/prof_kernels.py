@@ -80,6 +80,7 @@ if "nn" in which:
     timeit("nn_min 120k x 120k form1", lambda: ops.nn_min(x, y, 1, False), reps=3)
     timeit("nn_min_pair 120k x 120k form0 (both directions, one sweep)", lambda: ops.nn_min_pair(x, y, 0), reps=3)
     timeit("nn_min_pair 120k x 120k form1", lambda: ops.nn_min_pair(x, y, 1), reps=3)
+    timeit("nn_min_pair_arg 120k x 120k (both directions + both argmins, one sweep)", lambda: ops.nn_min_pair_arg(x, y), reps=3)
 if "enc" in which or "mlp" in which:
     torch.manual_seed(42)
     for prec in (0, 1):
