@@ -194,6 +194,20 @@ int pcst_knn_f32(const float* query, const float* ref, int B, int Q, int R, int 
 int pcst_knn_interpolate_f32(const float* feat, const int64_t* idx, const double* dist, int B, int R,
                              int Q, int k, int C, float* out, pcst_stream_t stream);
 
+/* ---- voxel-grid downsample: HierarchicalProcessor._voxel_grid_downsample_torch, models/diffusion_model.py:69-122 --
+ * (the step in front of the encoder and the denoiser on every 120k-point scan.)
+ * pcst_minmax_f32: out [B,6] = per-cloud (min x, min y, min z, max x, max y, max z), :78-79.
+ * pcst_voxel_representatives_f32: the deterministic part, :86-93.  xyz_min [B,3] and voxel_size [B] come from the
+ *   caller, which forms voxel_size with the reference's own scalar fp32 expression (:80-84).  Per cloud: voxel index
+ *   floor((p - min) / voxel_size).int(), int32 hash (ix*73856093)^(iy*19349663)^(iz*83492791), torch.unique order
+ *   (ascending signed hash), and per unique hash the truncated float32(sum of member indices) / float32(count).
+ *   rep [B,N] int64: the first count[b] entries of row b are valid.  The random thinning / top-up (:95-112) draws
+ *   from torch's generator and stays in the Python wrapper. */
+int pcst_minmax_f32(const float* xyz, int B, int N, float* out, pcst_stream_t stream);
+size_t pcst_voxel_representatives_workspace_bytes(int B, int N);
+int pcst_voxel_representatives_f32(const float* xyz, int B, int N, const float* xyz_min, const float* voxel_size,
+                                   int64_t* rep, int* count, void* ws, size_t ws_bytes, pcst_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

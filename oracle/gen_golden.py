@@ -58,10 +58,50 @@ def i32(t):
     return t.numpy().astype(np.int32)
 
 
+def gen_voxel(HP):
+    """Voxel-grid downsample (models/diffusion_model.py:69-122): the reference's outputs with the true RNG (seeded),
+    and its per-voxel representative indices, exposed by running it once more with ``torch.randperm`` replaced by
+    the identity permutation and ``torch.unique`` wrapped to record the number of voxels."""
+    clouds = torch.cat([S.lidar_scan(2, 20000), S.uniform_cloud(17, 1, 20000) * 1.5], 0)   # [2,20000,3]
+    target = 5000
+    hp = HP(20000, target)
+    torch.manual_seed(77)
+    down, idx = hp.downsample(clouds)
+    real_randperm, real_unique = torch.randperm, torch.unique
+    counts = []
+
+    def unique_spy(*a, **k):
+        out = real_unique(*a, **k)
+        counts.append(int(out[0].numel()))
+        return out
+
+    torch.randperm = lambda n, device=None: torch.arange(n)
+    torch.unique = unique_spy
+    try:
+        _, idx_id = hp.downsample(clouds)
+    finally:
+        torch.randperm, torch.unique = real_randperm, real_unique
+    sizes = []
+    for b in range(2):
+        pts = clouds[b]
+        r = pts.max(axis=0)[0] - pts.min(axis=0)[0]
+        r[r < 1e-6] = 1.0
+        sizes.append(float((r.prod() / target) ** (1 / 3) * 1.2))
+    assert torch.equal(down, torch.stack([clouds[b][idx[b]] for b in range(2)]))
+    save("voxel_downsample", clouds=clouds.numpy(), target=np.int64(target), indices=i32(idx),
+         rep0=i32(idx_id[0, :counts[0]]), rep1=i32(idx_id[1, :counts[1]]), voxel_size=np.array(sizes, np.float32),
+         # a cloud that is already small enough is returned unchanged (:70-72)
+         small_indices=i32(HP(100, 200).downsample(clouds[:, :100])[1]))
+
+
 def main():
     torch.set_grad_enabled(False)
     os.makedirs(OUT, exist_ok=True)
     enc, losses, HP, metrics = load_reference()
+    if "--only-voxel" in sys.argv:
+        gen_voxel(HP)
+        return
+    gen_voxel(HP)
     M = metrics.PointCloudMetrics("cpu")
 
     # ---- C1: PointNet2Encoder 2x4096, eval, F=256 (models/pointnet2_encoder.py:114-131) ----

@@ -278,3 +278,62 @@ def uniformity_score(points, k: int = 8) -> float:
         mean = m.mean()
         scores.append(1.0 / (1.0 + m.std() / mean) if mean > 0 else 0.0)
     return float(np.mean(scores))
+
+
+def voxel_representatives(points_b, xyz_min, voxel_size) -> np.ndarray:
+    """Deterministic part of HierarchicalProcessor._voxel_grid_downsample_torch for ONE cloud
+    (models/diffusion_model.py:86-93): voxel index, int32 hash, torch.unique order, truncated float32 mean of
+    the member indices.  points_b [N,3] fp32, xyz_min [3] fp32, voxel_size fp32 scalar -> int64 [U]."""
+    p = _f32(points_b)
+    q = np.floor((p - _f32(xyz_min)) / np.float32(voxel_size)).astype(np.int32)          # :86
+    u = q.astype(np.uint32)                                                               # wrapping int32 multiply
+    h = (u[:, 0] * np.uint32(73856093)) ^ (u[:, 1] * np.uint32(19349663)) ^ (u[:, 2] * np.uint32(83492791))
+    h = h.view(np.int32)                                                                  # :87
+    _, inverse = np.unique(h, return_inverse=True)                                        # :89 (ascending, signed)
+    sums = np.zeros(inverse.max() + 1, np.int64)
+    np.add.at(sums, inverse, np.arange(len(p), dtype=np.int64))                           # :91-92
+    counts = np.bincount(inverse).astype(np.int64)
+    return (sums.astype(np.float32) / counts.astype(np.float32)).astype(np.int64)         # :93 (float32 true division)
+
+
+def voxel_size_like_reference(points_b, target_size: int) -> np.float32:
+    """voxel_size of models/diffusion_model.py:78-85: fp32 range / product / division; the cube root of the
+    0-dim tensor is evaluated by torch in double and rounded to fp32 (pinned in tests/test_oracle_golden.py against
+    torch's own expression on random clouds), then multiplied by fp32(1.2)."""
+    p = _f32(points_b)
+    rng = p.max(axis=0) - p.min(axis=0)
+    rng = np.where(rng < np.float32(1e-6), np.float32(1.0), rng).astype(np.float32)
+    prod = np.float32(np.float32(rng[0] * rng[1]) * rng[2])
+    x = np.float32(prod / np.float32(target_size))
+    vs = np.float32(np.float32(float(x) ** (1 / 3)) * np.float32(1.2))
+    return np.float32(1e-3) if vs < 1e-6 else vs
+
+
+def voxel_grid_downsample(points, target_size: int, randperm) -> np.ndarray:
+    """HierarchicalProcessor._voxel_grid_downsample_torch (models/diffusion_model.py:69-122) -> indices [B,target].
+    ``randperm(n)`` must return the permutation the reference would draw at that point (the tests pass
+    ``lambda n: torch.randperm(n).numpy()`` after seeding torch like the reference run)."""
+    points = _f32(points)
+    B, N, _ = points.shape
+    if N <= target_size:
+        return np.broadcast_to(np.arange(N, dtype=np.int64), (B, N)).copy()
+    out = []
+    for b in range(B):
+        pts = points[b]
+        rep = voxel_representatives(pts, pts.min(axis=0), voxel_size_like_reference(pts, target_size))
+        cur = len(rep)
+        if cur > target_size:
+            final = rep[randperm(cur)[:target_size]]
+        elif cur < target_size:
+            mask = np.ones(N, bool)
+            mask[rep] = False
+            pool = np.arange(N, dtype=np.int64)[mask]
+            if len(pool) > 0:
+                k = min(target_size - cur, len(pool))
+                final = np.concatenate([rep, pool[randperm(len(pool))[:k]]])
+            else:
+                final = rep
+        else:
+            final = rep
+        out.append(final)
+    return np.stack(out)

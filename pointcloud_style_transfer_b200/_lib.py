@@ -70,6 +70,10 @@ SIGNATURES = {
                              c_void_p]),
     "pcst_knn_interpolate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p]),
+    "pcst_minmax_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "pcst_voxel_representatives_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pcst_voxel_representatives_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_size_t, c_void_p]),
 }
 
 _lib = None

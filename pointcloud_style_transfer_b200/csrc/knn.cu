@@ -4,31 +4,35 @@
 // 133-152: .cpu().numpy(), sklearn kd-tree build + query in fp64, numpy weights, .to(device)) and
 // the sklearn kNN of coverage_score / uniformity_score (evaluation/metrics.py:126-127,152-153).
 //
-// Parity target is sklearn's fp64 result, so distances are evaluated in fp64 in sklearn's
-// summation order, r = ((dx*dx) + (dy*dy)) + (dz*dz), with explicit non-fused double intrinsics;
-// the k best (r, j) per query are kept sorted in registers (strict <, ascending j => ties to the
-// lower index).  One thread per query; reference points are staged through shared memory as
-// double3 tiles shared by the whole CTA.  Bound: FP64 CUDA cores (8 DP ops per pair); HBM traffic
-// is negligible.  B200 executes FP64 at half the FP32 rate, which keeps the exact evaluation cheap
-// enough (90k x 30k pairs ~ 2.2e10 DP ops).
+// Parity target is sklearn's fp64 result, so the k best (r, j) per query are ranked on distances evaluated in
+// fp64 in sklearn's summation order, r = ((dx*dx) + (dy*dy)) + (dz*dz), with explicit non-fused double intrinsics;
+// the list stays sorted in registers (strict <, ascending j => ties to the lower index).  Almost every pair is
+// rejected earlier by an fp32 PREFILTER: d32 = fma(dz,dz, fma(dy,dy, dx*dx)) carries a relative error below
+// 5 * 2^-24, so a candidate whose exact distance beats the current k-th best always satisfies
+// d32 <= roundup(kth_best) * (1 + 2e-6); only those (a few dozen per query: the list converges like a
+// running minimum) pay the fp64 evaluation and the insertion.  Results are therefore identical to the all-fp64
+// sweep, at FP32-pipe speed.  One thread per query; reference points are staged through shared memory as
+// float4 tiles shared by the whole CTA (one broadcast LDS.128 per pair).
+// Bound: FP32 CUDA cores (6 FP32-pipe operations per pair); HBM traffic is negligible.
 #include "common.cuh"
 
 namespace pcst {
 
 constexpr int kKnnThreads = 128;
-constexpr int kKnnTile = 512;  // reference points per shared-memory tile (12 KiB as double)
+constexpr int kKnnTile = 1024;  // reference points per shared-memory tile (16 KiB as float4)
 constexpr int kKnnMaxK = 16;
 
 template <int KMAX>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q, int R, int k,
            int64_t* __restrict__ idx, double* __restrict__ dist) {
-    __shared__ double rx[kKnnTile], ry[kKnnTile], rz[kKnnTile];
+    __shared__ __align__(16) float4 tile[kKnnTile];
     const int b = blockIdx.y;
     const int q = blockIdx.x * kKnnThreads + threadIdx.x;
     const bool active = q < Q;
     const float* qp = query + ((size_t)b * Q + (active ? q : 0)) * 3;
-    const double qx = qp[0], qy = qp[1], qz = qp[2];
+    const float fx = qp[0], fy = qp[1], fz = qp[2];
+    const double qx = fx, qy = fy, qz = fz;
     const float* rp = ref + (size_t)b * R * 3;
 
     double bd[KMAX];
@@ -38,34 +42,41 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q
         bd[t] = __longlong_as_double(0x7ff0000000000000ll);  // +inf
         bi[t] = 0;
     }
+    float thr = __int_as_float(0x7f800000);  // fp32 upper bound of bd[KMAX - 1]
 
     for (int j0 = 0; j0 < R; j0 += kKnnTile) {
         const int n = R - j0 < kKnnTile ? R - j0 : kKnnTile;
         __syncthreads();
         for (int t = threadIdx.x; t < n; t += kKnnThreads) {
-            rx[t] = (double)rp[(size_t)(j0 + t) * 3];
-            ry[t] = (double)rp[(size_t)(j0 + t) * 3 + 1];
-            rz[t] = (double)rp[(size_t)(j0 + t) * 3 + 2];
+            const float* p = rp + (size_t)(j0 + t) * 3;
+            tile[t] = make_float4(p[0], p[1], p[2], 0.f);
         }
         __syncthreads();
         if (!active) continue;
+#pragma unroll 4
         for (int t = 0; t < n; ++t) {
-            const double dx = __dsub_rn(qx, rx[t]), dy = __dsub_rn(qy, ry[t]), dz = __dsub_rn(qz, rz[t]);
-            const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (d < bd[KMAX - 1]) {
-                // sorted insertion, fully unrolled so the list stays in registers
-                double cd = d;
-                int ci = j0 + t;
+            const float4 c = tile[t];
+            const float ex = fx - c.x, ey = fy - c.y, ez = fz - c.z;
+            const float d32 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+            if (d32 <= thr) {
+                const double dx = __dsub_rn(qx, (double)c.x), dy = __dsub_rn(qy, (double)c.y), dz = __dsub_rn(qz, (double)c.z);
+                const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (d < bd[KMAX - 1]) {
+                    // sorted insertion, fully unrolled so the list stays in registers
+                    double cd = d;
+                    int ci = j0 + t;
 #pragma unroll
-                for (int u = 0; u < KMAX; ++u) {
-                    if (cd < bd[u]) {
-                        const double td = bd[u];
-                        const int ti = bi[u];
-                        bd[u] = cd;
-                        bi[u] = ci;
-                        cd = td;
-                        ci = ti;
+                    for (int u = 0; u < KMAX; ++u) {
+                        if (cd < bd[u]) {
+                            const double td = bd[u];
+                            const int ti = bi[u];
+                            bd[u] = cd;
+                            bi[u] = ci;
+                            cd = td;
+                            ci = ti;
+                        }
                     }
+                    thr = __fmul_ru(__double2float_ru(bd[KMAX - 1]), 1.000002f);  // +inf stays +inf
                 }
             }
         }

@@ -53,7 +53,7 @@ def _workspace(nbytes: int, device) -> Tensor:
 KERNELS_PER_CALL = {"pcst_l2_prefetch": 1, "pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
                     "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 7, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_nn_min_pair_arg_f32": 6, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
-                    "pcst_knn_interpolate_f32": 1}
+                    "pcst_knn_interpolate_f32": 1, "pcst_minmax_f32": 1, "pcst_voxel_representatives_f32": 2}
 launch_count = 0
 _event_log = None  # None = off; else list of (name, start_event, end_event)
 
@@ -513,3 +513,47 @@ def knn_interpolate(feat: Tensor, idx: Tensor, dist: Tensor) -> Tensor:
 @knn_interpolate.register_fake
 def _(feat, idx, dist):
     return feat.new_empty(feat.shape[0], idx.shape[1], feat.shape[2], dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------- voxel-grid downsample
+
+
+@torch.library.custom_op("pcst::minmax", mutates_args=(), device_types="cuda")
+def minmax(xyz: Tensor) -> Tensor:
+    """xyz [B,N,3] -> [B,6] = (min x, min y, min z, max x, max y, max z) per cloud."""
+    _need_cuda(xyz)
+    xyz = _f32c(xyz)
+    B, N, _ = xyz.shape
+    out = torch.empty(B, 6, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _call("pcst_minmax_f32", _p(xyz), B, N, _p(out), _stream())
+    return out
+
+
+@minmax.register_fake
+def _(xyz):
+    return xyz.new_empty(xyz.shape[0], 6, dtype=torch.float32)
+
+
+@torch.library.custom_op("pcst::voxel_representatives", mutates_args=(), device_types="cuda")
+def voxel_representatives(xyz: Tensor, xyz_min: Tensor, voxel_size: Tensor) -> Tuple[Tensor, Tensor]:
+    """Deterministic part of the reference's voxel-grid downsample (models/diffusion_model.py:86-93).
+    xyz [B,N,3], xyz_min [B,3], voxel_size [B] -> (rep [B,N] int64, count [B] int32): row b's first count[b]
+    entries are the per-voxel mean point indices in torch.unique (ascending hash) order."""
+    lib = _lib.load()
+    _need_cuda(xyz, xyz_min, voxel_size)
+    xyz, xyz_min, voxel_size = _f32c(xyz), _f32c(xyz_min), _f32c(voxel_size)
+    B, N, _ = xyz.shape
+    rep = torch.empty(B, N, dtype=torch.int64, device=xyz.device)
+    count = torch.empty(B, dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        ws = _workspace(lib.pcst_voxel_representatives_workspace_bytes(B, N), xyz.device)
+        _call("pcst_voxel_representatives_f32", _p(xyz), B, N, _p(xyz_min), _p(voxel_size), _p(rep), _p(count), _p(ws),
+              ws.numel(), _stream())
+    return rep, count
+
+
+@voxel_representatives.register_fake
+def _(xyz, xyz_min, voxel_size):
+    B, N = xyz.shape[0], xyz.shape[1]
+    return xyz.new_empty(B, N, dtype=torch.int64), xyz.new_empty(B, dtype=torch.int32)

@@ -619,3 +619,51 @@ def test_coverage_uniformity_golden(api, dev, golden):
     assert abs(M.coverage_score(p, t, 0.01) - float(g["coverage_001"])) < 1e-12
     assert abs(M.uniformity_score(p, 8) - float(g["uniformity_8"])) < 1e-9
     assert abs(M.uniformity_score(t, 4) - float(g["uniformity_4"])) < 1e-9
+
+
+# ------------------------------------------------------------------------- voxel-grid downsample (next row)
+
+
+def test_voxel_downsample_golden_and_oracle(api, dev, golden, oracle):
+    """HierarchicalProcessor.downsample (models/diffusion_model.py:69-125) against the reference's own outputs:
+    per-voxel representatives bit-exact, and the final indices / points with the reference's RNG stream."""
+    g = golden("voxel_downsample")
+    target = int(g["target"])
+    clouds = torch.from_numpy(g["clouds"]).to(dev)
+    box = api.ops.minmax(clouds).cpu().numpy()
+    assert np.array_equal(box[:, :3], g["clouds"].min(axis=1)) and np.array_equal(box[:, 3:], g["clouds"].max(axis=1))
+    rep, count = api.ops.voxel_representatives(clouds, torch.from_numpy(box[:, :3]).to(dev),
+                                               torch.from_numpy(g["voxel_size"]).to(dev))
+    for b in range(2):
+        assert int(count[b]) == len(g["rep%d" % b])
+        assert np.array_equal(rep[b, :int(count[b])].cpu().numpy(), g["rep%d" % b])
+    hp = api.dm.HierarchicalProcessor(20000, target)
+    torch.manual_seed(77)
+    down, idx = hp.downsample(clouds)
+    assert idx.dtype == torch.int64 and idx.shape == (2, target) and down.shape == (2, target, 3)
+    assert np.array_equal(idx.cpu().numpy(), g["indices"])
+    assert torch.equal(down, torch.stack([clouds[b][idx[b]] for b in range(2)]))
+    small, sidx = api.dm.HierarchicalProcessor(100, 200).downsample(clouds[:, :100])
+    assert np.array_equal(sidx.cpu().numpy(), g["small_indices"]) and torch.equal(small, clouds[:, :100])
+
+
+@pytest.mark.parametrize("B,N,target", [(1, 120000, 30000), (3, 4097, 1000), (2, 333, 50), (1, 1500, 1499)])
+def test_voxel_representatives_sizes_against_oracle(api, dev, oracle, B, N, target):
+    """The product shape (one 120k scan -> 30k) and ragged sizes: hash, sort order and index means against the
+    numpy restatement; degenerate axis (all z equal) exercises the range clamp (:81)."""
+    x = (S.lidar_scan(5, N) if N > 100000 else S.uniform_cloud(N, B, N)).clone()
+    if N == 333:
+        x[..., 2] = 0.25
+    box = api.ops.minmax(x.to(dev)).cpu()
+    sizes = np.array([oracle.voxel_size_like_reference(x[b].numpy(), target) for b in range(B)], np.float32)
+    rep, count = api.ops.voxel_representatives(x.to(dev), box[:, :3].to(dev), torch.from_numpy(sizes).to(dev))
+    for b in range(B):
+        ref = oracle.voxel_representatives(x[b].numpy(), x[b].numpy().min(axis=0), sizes[b])
+        assert int(count[b]) == len(ref)
+        assert np.array_equal(rep[b, :len(ref)].cpu().numpy(), ref)
+    hp = api.dm.HierarchicalProcessor(N, target)
+    torch.manual_seed(5)
+    _, idx = hp.downsample(x.to(dev))
+    torch.manual_seed(5)
+    ref_idx = oracle.voxel_grid_downsample(x.numpy(), target, lambda n: torch.randperm(n).numpy())
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)

@@ -99,3 +99,37 @@ def test_upsample_knn_and_sklearn_metrics(golden, oracle):
     assert abs(oracle.coverage_score(g["pred"], g["target"], 0.01) - float(g["coverage_001"])) < 1e-12
     assert abs(oracle.uniformity_score(g["pred"], 8) - float(g["uniformity_8"])) < 1e-9
     assert abs(oracle.uniformity_score(g["target"], 4) - float(g["uniformity_4"])) < 1e-9
+
+
+def test_voxel_downsample_oracle_against_reference_golden(golden, oracle):
+    """models/diffusion_model.py:69-122: representatives (deterministic part) bit-exact; the full function with the
+    reference's RNG stream reproduces the reference's indices."""
+    import torch
+
+    g = golden("voxel_downsample")
+    target = int(g["target"])
+    for b in range(2):
+        pts = g["clouds"][b]
+        vs = oracle.voxel_size_like_reference(pts, target)
+        assert vs.tobytes() == g["voxel_size"][b].tobytes()
+        assert np.array_equal(oracle.voxel_representatives(pts, pts.min(axis=0), vs), g["rep%d" % b])
+    torch.manual_seed(77)
+    idx = oracle.voxel_grid_downsample(g["clouds"], target, lambda n: torch.randperm(n).numpy())
+    assert np.array_equal(idx, g["indices"])
+    assert np.array_equal(oracle.voxel_grid_downsample(g["clouds"][:, :100], 200, None), g["small_indices"])
+
+
+def test_voxel_size_scalar_arithmetic_matches_torch(oracle):
+    """The oracle's numpy restatement of the 0-dim tensor expression (:80-84) against torch's own evaluation."""
+    import torch
+
+    rs = np.random.RandomState(3)
+    for _ in range(300):
+        n = int(rs.randint(50, 400))
+        pts = (rs.randn(n, 3) * rs.uniform(0.01, 30.0, size=3)).astype(np.float32)
+        target = int(rs.randint(5, 40))
+        t = torch.from_numpy(pts)
+        r = t.max(axis=0)[0] - t.min(axis=0)[0]
+        r[r < 1e-6] = 1.0
+        ref = ((r.prod() / target) ** (1 / 3) * 1.2).numpy()
+        assert oracle.voxel_size_like_reference(pts, target).tobytes() == np.float32(ref).tobytes()

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pointcloud_style_transfer_b200 import ops, synthetic as S  # noqa: E402
 from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder  # noqa: E402
 
-which = set(sys.argv[1:]) or {"fps", "ball", "nn", "mlp", "enc", "knn"}
+which = set(sys.argv[1:]) or {"fps", "ball", "nn", "mlp", "enc", "knn", "vox"}
 dev = torch.device("cuda:0")
 x = S.lidar_scan(0).to(dev)
 y = S.lidar_scan(100).to(dev)
@@ -94,3 +94,13 @@ if "enc" in which or "mlp" in which:
 if "knn" in which:
     q, r = S.uniform_cloud(1, 1, 90000).to(dev), S.uniform_cloud(2, 1, 30000).to(dev)
     timeit("knn 90k x 30k k=3", lambda: ops.knn(q, r, 3), reps=2)
+if "vox" in which:
+    from pointcloud_style_transfer_b200.models.diffusion_model import HierarchicalProcessor
+    hp = HierarchicalProcessor(120000, 30000)
+    box = ops.minmax(x)
+    vs = torch.tensor([0.05], device=dev)
+    timeit("minmax 120k", lambda: ops.minmax(x))
+    timeit("voxel_representatives 120k (hash + radix sort + run means)", lambda: ops.voxel_representatives(x, box[:, :3].contiguous(), vs))
+    timeit("HierarchicalProcessor.downsample 120k -> 30k (incl. host scalar math, randperm, gathers)", lambda: hp.downsample(x), reps=3)
+    q9 = S.lidar_scan(3)
+    timeit("knn self 120k x 120k k=9 (uniformity_score)", lambda: ops.knn(x, x, 9), reps=2)
