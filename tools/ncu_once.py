@@ -27,6 +27,8 @@ for rep in range(2):  # pass 0 warms up (module load, function attributes), pass
         ops.nn_min(x, y, 0, False)      # Chamfer direction, loss form
         ops.nn_min(x, y, 0, True)       # with argmin (training)
         ops.nn_min_pair(x, y, 0)        # both Chamfer directions in one sweep
+        ops.nn_min_pair_arg(x, y)       # ... with both argmins (training)
         ops.knn(q, r, 3)                # upsample_knn search
+        ops.voxel_representatives(x, ops.minmax(x)[:, :3].contiguous(), torch.tensor([0.05], device=dev))
     torch.cuda.synchronize()
 print("ncu_once ok")
