@@ -8,11 +8,12 @@
 // point indices, formed as float32(sum) / float32(count) and truncated (:90-93).  The random top-up / thinning
 // (:95-112) draws from torch's CPU generator and stays in the Python wrapper.
 //
-// Here: one launch for the bounding boxes, one for the hashes, and one CTA per cloud that sorts (hash, index)
-// pairs with a stable 4-bit LSD radix sort (8 passes; coalesced 32-key rounds per warp, ballot-built digit groups for the
-// per-(digit, warp) histogram and the in-round ranks, block-wide scan) and then reduces each run of equal hashes.
-// Everything is integer work except the index division, which reproduces torch's int64 / int64 -> float32 true division.  Bound: latency of the 8 dependent passes over
-// N * 8 B of L2-resident keys (HBM traffic N*12 B in, U*8 B out).
+// Here: one launch for the bounding boxes, one for the hashes, a stable 8-bit LSD radix sort of the (hash, index) pairs
+// spread over ceil(N / 4096) CTAs per cloud (4 passes x {count, scatter}; coalesced 32-key rounds per warp, ballot-built
+// digit groups for the per-(digit, warp) counters and the in-round ranks) and two launches that reduce each run of
+// equal hashes.  Everything is integer work except the index division, which reproduces torch's int64 / int64 ->
+// float32 true division.  Bound: launch latency of the 11 small dependent launches (N*8 B of L2-resident keys per
+// pass; HBM traffic N*12 B in, U*8 B out).
 #include "common.cuh"
 
 namespace pcst {
@@ -81,12 +82,23 @@ __global__ void vox_hash_kernel(const float* __restrict__ xyz, int N, const floa
     vals[(size_t)b * N + i] = (unsigned int)i;
 }
 
-// lanes of the warp that are in range and hold the same 4-bit digit as this lane: four ballots, one per digit bit
-// (MATCH.ANY computes the same mask but is issued at a small fraction of the VOTE rate)
-__device__ __forceinline__ unsigned int digit_peers(unsigned int d, bool in) {
+// ---- stable LSD radix sort of (key, val), 8-bit digits, a cloud spread over ceil(N / 4096) CTAs -----------------
+// Per pass: vox_count_kernel writes every tile's digit histogram to ghist[b][digit][tile]; vox_scatter_kernel
+// turns the table into its own global bases (digit-major exclusive scan: all smaller digits of all tiles, then the
+// same digit of the earlier tiles -- 256 threads, a few dozen loads each), ranks the tile's keys stably and
+// scatters them.  Inside a tile warp w owns a contiguous 512-key segment and walks it 32 keys at a time; lanes holding
+// the same digit find each other with eight ballots (one per digit bit): the group's size feeds the per-(digit,
+// warp) counter, a lane's rank inside its group gives its slot, and scanning the counters in (digit, warp) order
+// keeps the order of equal digits across warps.
+constexpr int kSortTile = 4096;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortRounds = kSortTile / kSortThreads;  // 32-key rounds per warp: 16
+
+__device__ __forceinline__ unsigned int digit_peers8(unsigned int d, bool in) {
     unsigned int peers = __ballot_sync(0xffffffffu, in);
 #pragma unroll
-    for (int bit = 0; bit < 4; ++bit) {
+    for (int bit = 0; bit < 8; ++bit) {
         const bool set = (d >> bit) & 1u;
         const unsigned int bal = __ballot_sync(0xffffffffu, set);
         peers &= set ? bal : ~bal;
@@ -94,142 +106,163 @@ __device__ __forceinline__ unsigned int digit_peers(unsigned int d, bool in) {
     return peers;
 }
 
-// ---- one CTA per cloud: stable LSD radix sort of (key, val), then the per-run index mean -----------------------
-// Warp w owns the contiguous segment [w * seg, (w + 1) * seg) and walks it 32 keys at a time (coalesced).  Inside
-// a round, lanes holding the same 4-bit digit find each other with four ballots: the group's size feeds the
-// per-(digit, warp) histogram, a lane's rank inside its group gives its stable output slot.  The 16 x 32 counters
-// are scanned in (digit, warp) order, which makes the scatter stable across warps as well.
-__global__ void __launch_bounds__(kVoxThreads)
-vox_sort_reduce_kernel(unsigned int* __restrict__ keys0, unsigned int* __restrict__ vals0,
-                       unsigned int* __restrict__ keys1, unsigned int* __restrict__ vals1, int N,
-                       int64_t* __restrict__ rep, int* __restrict__ count) {
-    constexpr int kWarps = kVoxThreads / 32;
-    constexpr int kU = 8;  // rounds whose loads are issued together
-    __shared__ unsigned int hist[16 * kWarps];  // [digit][warp]
-    __shared__ unsigned int warp_sums[kWarps];
-    __shared__ unsigned int total_sh;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__global__ void __launch_bounds__(kSortThreads)
+vox_count_kernel(const unsigned int* __restrict__ keys, int N, int shift, unsigned int* __restrict__ ghist, int ntiles) {
+    __shared__ unsigned int hist[256];
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    hist[tid] = 0;
+    __syncthreads();
+    const unsigned int* k = keys + (size_t)b * N;
+    const int lo = tile * kSortTile, hi = min(lo + kSortTile, N);
+    for (int i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&hist[(k[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    ghist[((size_t)b * 256 + tid) * ntiles + tile] = hist[tid];
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+vox_scatter_kernel(const unsigned int* __restrict__ kin, const unsigned int* __restrict__ vin,
+                   unsigned int* __restrict__ kout, unsigned int* __restrict__ vout, int N, int shift,
+                   const unsigned int* __restrict__ ghist, int ntiles) {
+    __shared__ unsigned int wcnt[256 * kSortWarps];  // [digit][warp]
+    __shared__ unsigned int warp_sums[kSortWarps];
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    unsigned int* kin = keys0 + (size_t)b * N;
-    unsigned int* vin = vals0 + (size_t)b * N;
-    unsigned int* kout = keys1 + (size_t)b * N;
-    unsigned int* vout = vals1 + (size_t)b * N;
-    const int seg = ((N + kWarps - 1) / kWarps + 31) / 32 * 32;
-    const int wlo = min(warp * seg, N), whi = min(wlo + seg, N);
+    const size_t off = (size_t)b * N;
 
-    // block-wide exclusive scan of one value per thread (returns the exclusive prefix; total in total_sh)
-    auto block_exscan = [&](unsigned int v) -> unsigned int {
-        unsigned int incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
+    // global base of (digit = tid, this tile)
+    unsigned int total = 0, before = 0;
+    {
+        const unsigned int* g = ghist + ((size_t)b * 256 + tid) * ntiles;
+        for (int c = 0; c < ntiles; ++c) {
+            const unsigned int h = g[c];
+            before += c < tile ? h : 0u;
+            total += h;
         }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned int w = warp_sums[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int u = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += u;
-            }
-            warp_sums[lane] = wi - w;
-            if (lane == 31) total_sh = wi;
-        }
-        __syncthreads();
-        const unsigned int r = warp_sums[warp] + incl - v;
-        __syncthreads();  // warp_sums / total_sh are reused by the next call
-        return r;
-    };
-
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 4 * pass;
-        if (tid < 16 * kWarps) hist[tid] = 0;
-        __syncthreads();
-        for (int i0 = wlo; i0 < whi; i0 += 32 * kU) {
-            unsigned int kk[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {  // kU independent coalesced loads in flight before the dependent part
-                const int i = i0 + u * 32 + lane;
-                kk[u] = i < whi ? kin[i] : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int i = i0 + u * 32 + lane;
-                const bool in = i < whi;
-                const unsigned int d = (kk[u] >> shift) & 15u;
-                const unsigned int peers = digit_peers(d, in);
-                if (in && (peers & lt_mask) == 0) hist[d * kWarps + warp] += __popc(peers);  // group leader; warp-private column
-                __syncwarp();  // the next round's leader of the same digit may be another lane
-            }
-        }
-        __syncthreads();
-        // exclusive scan of the 512 counters in (digit, warp) order
-        const unsigned int mine = tid < 16 * kWarps ? hist[tid] : 0u;
-        const unsigned int ex = block_exscan(mine);
-        if (tid < 16 * kWarps) hist[tid] = ex;
-        __syncthreads();
-        for (int i0 = wlo; i0 < whi; i0 += 32 * kU) {
-            unsigned int kk[kU], vv[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int i = i0 + u * 32 + lane;
-                kk[u] = vv[u] = 0u;
-                if (i < whi) {
-                    kk[u] = kin[i];
-                    vv[u] = vin[i];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int i = i0 + u * 32 + lane;
-                const bool in = i < whi;
-                const unsigned int d = (kk[u] >> shift) & 15u;
-                const unsigned int peers = digit_peers(d, in);
-                unsigned int pos = 0;
-                if (in) pos = hist[d * kWarps + warp] + __popc(peers & lt_mask);
-                __syncwarp();
-                if (in && (peers & lt_mask) == 0) hist[d * kWarps + warp] += __popc(peers);
-                __syncwarp();
-                if (in) {
-                    kout[pos] = kk[u];
-                    vout[pos] = vv[u];
-                }
-            }
-        }
-        __syncthreads();
-        unsigned int* t0 = kin; kin = kout; kout = t0;
-        unsigned int* t1 = vin; vin = vout; vout = t1;
     }
-    // after 8 passes (an even number) the sorted data is back in keys0 / vals0 (= kin / vin)
+    unsigned int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) wcnt[tid * kSortWarps + w] = 0;
+    __syncthreads();
+    unsigned int base = incl - total + before;
+    for (int w = 0; w < warp; ++w) base += warp_sums[w];
 
-    // run heads -> run ids (ordered: warp segments, then rounds, then lanes) -> one mean per run
+    // the tile's keys stay in registers between the counting and the scattering sweep
+    const int wlo = tile * kSortTile + warp * (kSortTile / kSortWarps);
+    unsigned int kk[kSortRounds], vv[kSortRounds];
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int i = wlo + r * 32 + lane;
+        kk[r] = vv[r] = 0u;
+        if (i < N) {
+            kk[r] = kin[off + i];
+            vv[r] = vin[off + i];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const bool in = wlo + r * 32 + lane < N;
+        const unsigned int d = (kk[r] >> shift) & 255u;
+        const unsigned int peers = digit_peers8(d, in);
+        if (in && (peers & lt_mask) == 0) wcnt[d * kSortWarps + warp] += __popc(peers);  // leader; warp-private column
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit = tid: exclusive scan over the warps, starting at the global base
+        unsigned int run = base;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const unsigned int t = wcnt[tid * kSortWarps + w];
+            wcnt[tid * kSortWarps + w] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const bool in = wlo + r * 32 + lane < N;
+        const unsigned int d = (kk[r] >> shift) & 255u;
+        const unsigned int peers = digit_peers8(d, in);
+        unsigned int pos = 0;
+        if (in) pos = wcnt[d * kSortWarps + warp] + __popc(peers & lt_mask);
+        __syncwarp();
+        if (in && (peers & lt_mask) == 0) wcnt[d * kSortWarps + warp] += __popc(peers);
+        __syncwarp();
+        if (in) {
+            kout[off + pos] = kk[r];
+            vout[off + pos] = vv[r];
+        }
+    }
+}
+
+// ---- runs of equal keys -> one truncated float32 mean of the member indices per run ---------------------------
+__global__ void __launch_bounds__(kSortThreads)
+vox_heads_kernel(const unsigned int* __restrict__ keys, int N, unsigned int* __restrict__ gcount, int ntiles) {
+    __shared__ unsigned int wsum[kSortWarps];
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int* k = keys + (size_t)b * N;
+    const int lo = tile * kSortTile, hi = min(lo + kSortTile, N);
     unsigned int heads = 0;
-    for (int i0 = wlo; i0 < whi; i0 += 32) {
-        const int i = i0 + lane;
-        const bool head = i < whi && (i == 0 || kin[i] != kin[i - 1]);
-        heads += __popc(__ballot_sync(0xffffffffu, head));  // every lane counts the whole round
+    for (int i = lo + tid; i < hi; i += kSortThreads) heads += (i == 0 || k[i] != k[i - 1]) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) heads += __shfl_xor_sync(0xffffffffu, heads, o);
+    if (lane == 0) wsum[warp] = heads;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < kSortWarps; ++w) t += wsum[w];
+        gcount[(size_t)b * ntiles + tile] = t;
     }
-    unsigned int run = block_exscan(lane == 0 ? heads : 0u);  // lane 0 of each warp contributes the warp's count
-    run = __shfl_sync(0xffffffffu, run, 0);
-    if (tid == 0) count[b] = (int)total_sh;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+vox_runs_kernel(const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals, int N,
+                const unsigned int* __restrict__ gcount, int ntiles, int64_t* __restrict__ rep, int* __restrict__ count) {
+    __shared__ unsigned int wsum[kSortWarps];
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const unsigned int* k = keys + (size_t)b * N;
+    const unsigned int* v = vals + (size_t)b * N;
+    unsigned int before = 0, total = 0;
+    for (int c = 0; c < ntiles; ++c) {
+        const unsigned int h = gcount[(size_t)b * ntiles + c];
+        before += c < tile ? h : 0u;
+        total += h;
+    }
+    if (tile == 0 && tid == 0) count[b] = (int)total;
+    const int wlo = tile * kSortTile + warp * (kSortTile / kSortWarps);
+    unsigned int hb[kSortRounds], mine = 0;
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int i = wlo + r * 32 + lane;
+        const bool head = i < N && (i == 0 || k[i] != k[i - 1]);
+        hb[r] = __ballot_sync(0xffffffffu, head);
+        mine += __popc(hb[r]);
+    }
+    if (lane == 0) wsum[warp] = mine;
+    __syncthreads();
+    unsigned int run = before;
+    for (int w = 0; w < warp; ++w) run += wsum[w];
     int64_t* out = rep + (size_t)b * N;
-    for (int i0 = wlo; i0 < whi; i0 += 32) {
-        const int i = i0 + lane;
-        const bool head = i < whi && (i == 0 || kin[i] != kin[i - 1]);
-        const unsigned int hb = __ballot_sync(0xffffffffu, head);
-        if (head) {
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int i = wlo + r * 32 + lane;
+        if ((hb[r] >> lane) & 1u) {
             long long s = 0, c = 0;
-            const unsigned int k = kin[i];
-            for (int j = i; j < N && kin[j] == k; ++j) {  // runs are short (a few points per voxel); may cross segments
-                s += vin[j];
+            const unsigned int key = k[i];
+            for (int j = i; j < N && k[j] == key; ++j) {  // runs are short (a few points per voxel); may cross tiles
+                s += v[j];
                 ++c;
             }
             // (sum / bincount).long() with int64 operands: torch true-divides in float32 (:93)
-            out[run + __popc(hb & lt_mask)] = (int64_t)__fdiv_rn((float)s, (float)c);
+            out[run + __popc(hb[r] & lt_mask)] = (int64_t)__fdiv_rn((float)s, (float)c);
         }
-        run += __popc(hb);
+        run += __popc(hb[r]);
     }
 }
 
@@ -246,7 +279,9 @@ extern "C" int pcst_minmax_f32(const float* xyz, int B, int N, float* out, pcst_
 
 extern "C" size_t pcst_voxel_representatives_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
-    return 4 * align_up((size_t)B * N * sizeof(unsigned int), 256);
+    const size_t ntiles = ((size_t)N + kSortTile - 1) / kSortTile;
+    return 4 * align_up((size_t)B * N * sizeof(unsigned int), 256) + align_up((size_t)B * 256 * ntiles * 4, 256) +
+           align_up((size_t)B * ntiles * 4, 256);
 }
 
 extern "C" int pcst_voxel_representatives_f32(const float* xyz, int B, int N, const float* xyz_min,
@@ -260,13 +295,27 @@ extern "C" int pcst_voxel_representatives_f32(const float* xyz, int B, int N, co
         set_error("pcst_voxel_representatives_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need);
         return PCST_ERR_WORKSPACE;
     }
+    const int ntiles = (N + kSortTile - 1) / kSortTile;
     const size_t stride = align_up((size_t)B * N * sizeof(unsigned int), 256);
     unsigned int* k0 = (unsigned int*)ws;
     unsigned int* v0 = (unsigned int*)((char*)ws + stride);
     unsigned int* k1 = (unsigned int*)((char*)ws + 2 * stride);
     unsigned int* v1 = (unsigned int*)((char*)ws + 3 * stride);
+    unsigned int* ghist = (unsigned int*)((char*)ws + 4 * stride);
+    unsigned int* gcount = (unsigned int*)((char*)ghist + align_up((size_t)B * 256 * ntiles * 4, 256));
     vox_hash_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(xyz, N, xyz_min, voxel_size, k0, v0);
     PCST_CUDA(cudaGetLastError());
-    vox_sort_reduce_kernel<<<B, kVoxThreads, 0, stream>>>(k0, v0, k1, v1, N, rep, count);
-    return check_cuda(cudaGetLastError(), "vox_sort_reduce_kernel");
+    const dim3 grid(ntiles, B);
+    for (int pass = 0; pass < 4; ++pass) {  // an even number of passes: the sorted data ends in k0 / v0
+        vox_count_kernel<<<grid, kSortThreads, 0, stream>>>(k0, N, 8 * pass, ghist, ntiles);
+        PCST_CUDA(cudaGetLastError());
+        vox_scatter_kernel<<<grid, kSortThreads, 0, stream>>>(k0, v0, k1, v1, N, 8 * pass, ghist, ntiles);
+        PCST_CUDA(cudaGetLastError());
+        unsigned int* t = k0; k0 = k1; k1 = t;
+        t = v0; v0 = v1; v1 = t;
+    }
+    vox_heads_kernel<<<grid, kSortThreads, 0, stream>>>(k0, N, gcount, ntiles);
+    PCST_CUDA(cudaGetLastError());
+    vox_runs_kernel<<<grid, kSortThreads, 0, stream>>>(k0, v0, N, gcount, ntiles, rep, count);
+    return check_cuda(cudaGetLastError(), "vox_runs_kernel");
 }

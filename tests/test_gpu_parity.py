@@ -667,3 +667,26 @@ def test_voxel_representatives_sizes_against_oracle(api, dev, oracle, B, N, targ
     torch.manual_seed(5)
     ref_idx = oracle.voxel_grid_downsample(x.numpy(), target, lambda n: torch.randperm(n).numpy())
     assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+def test_compare_calculate_similarity_against_oracle_and_scipy(api, dev, oracle):
+    """compare.py:6-43 (precision / recall / F1 over fp64 1-NN distances) against the oracle's fp64 brute force and,
+    when scipy is importable, against the cKDTree call the reference itself makes."""
+    from pointcloud_style_transfer_b200.compare import calculate_similarity
+
+    a = S.lidar_scan(4, 20000)[0].numpy()
+    b = (S.lidar_scan(4, 20000)[0] + 0.01 * torch.randn(20000, 3, generator=torch.Generator().manual_seed(9))).numpy()[:17000]
+    for thr in (0.2, 0.02, 0.005):
+        p, r, f = calculate_similarity(a, b, thr)
+        d21, _ = oracle.knn(b[None], a[None], 1)
+        d12, _ = oracle.knn(a[None], b[None], 1)
+        rp, rr = float(np.mean(d21[0, :, 0] < thr)), float(np.mean(d12[0, :, 0] < thr))
+        rf = 0.0 if rp + rr == 0 else 2 * rp * rr / (rp + rr)
+        assert (p, r, f) == (rp * 100, rr * 100, rf)
+        try:
+            from scipy.spatial import cKDTree
+        except ImportError:
+            continue
+        sp = float(np.mean(cKDTree(a).query(b, k=1)[0] < thr))
+        sr = float(np.mean(cKDTree(b).query(a, k=1)[0] < thr))
+        assert (p, r) == (sp * 100, sr * 100)

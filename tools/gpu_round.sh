@@ -29,7 +29,7 @@ if [ "${NCU:-0}" = "1" ]; then
   fi
   timeout 300 python tools/ncu_once.py > gpurun_out/plain_once.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:'fps_kernel|nn_min_kernel|nn_min_pair_kernel|nn_min_pair_arg_kernel|bq_mask_kernel|bq_emit_kernel|bq_small_kernel|sa_mlp_tc_kernel|mlp_layer_kernel|knn_kernel|vox_sort_reduce_kernel|vox_hash_kernel|minmax_kernel' \
+      -k regex:'fps_kernel|nn_min_kernel|nn_min_pair_kernel|nn_min_pair_arg_kernel|bq_mask_kernel|bq_emit_kernel|bq_small_kernel|sa_mlp_tc_kernel|mlp_layer_kernel|knn_kernel|vox_scatter_kernel|vox_hash_kernel|minmax_kernel' \
       -s ${NCU_SKIP:-30} -c ${NCU_COUNT:-30} -o gpurun_out/prof_full python tools/ncu_once.py > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"; tail -5 gpurun_out/ncu_full.log
 fi
