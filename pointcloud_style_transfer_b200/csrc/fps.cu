@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kFpsMaxThreads, 1)
 fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __restrict__ start,
            int64_t* __restrict__ out, float* __restrict__ new_xyz, int pts_per_cta, float* __restrict__ dist_ws,
            int prune, int log2c) {
-    extern __shared__ __align__(16) float smem_pts[];  // P > 0: SoA copy of this CTA's points
+    extern __shared__ __align__(16) float4 smem_pts[];  // P > 0: (x, y, z, -) copy of this CTA's points, one LDS.128 per look-up
     __shared__ FpsShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -82,9 +82,6 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         if (count > pts_per_cta) count = pts_per_cta;
         if (count < 0) count = 0;
     }
-    float* sx = smem_pts;
-    float* sy = smem_pts + nwarps * CH;
-    float* sz = smem_pts + 2 * nwarps * CH;
     float* gdist = (P == 0) ? dist_ws + (size_t)b * N + cbase : nullptr;
 
     constexpr int PP = P > 0 ? P / 2 : 1;
@@ -104,7 +101,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
                 if (cbase + l < N) {
                     const float* q = pts + (size_t)(cbase + l) * 3;
                     v[h][0] = q[0]; v[h][1] = q[1]; v[h][2] = q[2]; v[h][3] = 1e10f;
-                    sx[sbase + l] = v[h][0]; sy[sbase + l] = v[h][1]; sz[sbase + l] = v[h][2];
+                    smem_pts[sbase + l] = make_float4(v[h][0], v[h][1], v[h][2], 0.f);
                     mnx = fminf(mnx, v[h][0]); mxx = fmaxf(mxx, v[h][0]);
                     mny = fminf(mny, v[h][1]); mxy = fmaxf(mxy, v[h][1]);
                     mnz = fminf(mnz, v[h][2]); mxz = fmaxf(mxz, v[h][2]);
@@ -212,7 +209,8 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         if (C == 1 || prune == 5) {
             far = bidx;
             if (P > 0) {
-                cx = sx[bslot]; cy = sy[bslot]; cz = sz[bslot];
+                const float4 q4 = smem_pts[bslot];
+                cx = q4.x; cy = q4.y; cz = q4.z;
             } else {
                 const float* q = pts + (size_t)bidx * 3;
                 cx = q[0]; cy = q[1]; cz = q[2];
@@ -226,7 +224,8 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
                 float x = 0.f, y = 0.f, z = 0.f;
                 if (bidx != kNoIdx) {
                     if (P > 0) {
-                        x = sx[bslot]; y = sy[bslot]; z = sz[bslot];
+                        const float4 q4 = smem_pts[bslot];
+                        x = q4.x; y = q4.y; z = q4.z;
                     } else {
                         const float* q = pts + (size_t)bidx * 3;
                         x = q[0]; y = q[1]; z = q[2];
@@ -253,11 +252,18 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
             const int gb = __float_as_int(a.w);
             const int gmax = __reduce_max_sync(0xffffffffu, gb);
             const unsigned gidx = __reduce_min_sync(0xffffffffu, gb == gmax ? ii : kNoIdx);
-            const unsigned hit = __ballot_sync(0xffffffffu, ii == gidx);
-            const int wl = __ffs(hit) - 1;
-            cx = __shfl_sync(0xffffffffu, a.x, wl);
-            cy = __shfl_sync(0xffffffffu, a.y, wl);
-            cz = __shfl_sync(0xffffffffu, a.z, wl);
+            if (P > 0) {
+                // the winner's coordinates sit in the slot of the CTA that owns its chunk (chunk mod C): one
+                // broadcast LDS instead of a ballot and three shuffles
+                const float4 wp = sh.cslot[par][(gidx / CH) & (C - 1u)];
+                cx = wp.x; cy = wp.y; cz = wp.z;
+            } else {
+                const unsigned hit = __ballot_sync(0xffffffffu, ii == gidx);
+                const int wl = __ffs(hit) - 1;
+                cx = __shfl_sync(0xffffffffu, a.x, wl);
+                cy = __shfl_sync(0xffffffffu, a.y, wl);
+                cz = __shfl_sync(0xffffffffu, a.z, wl);
+            }
             far = gidx;
         }
     }
@@ -287,7 +293,7 @@ static FpsPlan fps_plan(int B, int N) {
     const long per_thread = (N + lanes - 1) / lanes;
     p.P = per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 8 ? 8 : per_thread <= 16 ? 16 : 0;
     p.pts_per_cta = p.P > 0 ? threads * p.P : (int)align_up((size_t)((N + C - 1) / C), 32);
-    p.smem = p.P > 0 ? (size_t)3 * p.pts_per_cta * sizeof(float) : 0;
+    p.smem = p.P > 0 ? (size_t)p.pts_per_cta * sizeof(float4) : 0;
     p.ws = p.P > 0 ? 0 : align_up((size_t)B * N * sizeof(float), 256);
     return p;
 }
