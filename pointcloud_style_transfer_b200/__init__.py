@@ -18,7 +18,8 @@ __version__ = "0.1.0"
 def patch_reference() -> None:
     """Replace the hot-path symbols of an importable reference checkout (``models.pointnet2_encoder``,
     ``models.losses``, ``evaluation.metrics`` and ``HierarchicalProcessor.upsample_knn``) with the
-    B200 implementations, so that the reference's trainer / inference scripts run unmodified."""
+    B200 implementations (plus the two "next" rows that are built: ``HierarchicalProcessor.downsample`` and
+    ``compare.calculate_similarity``), so that the reference's trainer / inference scripts run unmodified."""
     import importlib
 
     from .evaluation import metrics as our_metrics
@@ -36,6 +37,11 @@ def patch_reference() -> None:
     ref_dm = importlib.import_module("models.diffusion_model")
     ref_dm.PointNet2Encoder = our_enc.PointNet2Encoder
     ref_dm.HierarchicalProcessor.upsample_knn = our_dm.HierarchicalProcessor.upsample_knn
+    for name in ("rng_device", "_randperm", "_voxel_grid_downsample_torch", "downsample"):
+        setattr(ref_dm.HierarchicalProcessor, name, getattr(our_dm.HierarchicalProcessor, name))
+    if "compare" in sys.modules:
+        from . import compare as our_compare
+        sys.modules["compare"].calculate_similarity = our_compare.calculate_similarity
     if "evaluation.metrics" in sys.modules:
         sys.modules["evaluation.metrics"].PointCloudMetrics = our_metrics.PointCloudMetrics
     for mod in ("training.trainer", "scripts.test"):

@@ -690,3 +690,45 @@ def test_compare_calculate_similarity_against_oracle_and_scipy(api, dev, oracle)
         sp = float(np.mean(cKDTree(a).query(b, k=1)[0] < thr))
         sr = float(np.mean(cKDTree(b).query(a, k=1)[0] < thr))
         assert (p, r) == (sp * 100, sr * 100)
+
+
+# ------------------------------------------------------------------------------------ randomised shapes
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_against_oracle(api, dev, oracle, seed):
+    """Randomised batch sizes / point counts / radii (odd sizes, B up to 9 = more clouds than concurrent FPS
+    clusters, N not a multiple of 4 so the TMA-staged ball-query tiles take the misaligned path, lattice clouds for
+    ties): FPS, ball query, one-sweep NN-min with argmins and kNN against the oracle, everything bit-exact."""
+    rs = np.random.RandomState(1000 + seed)
+    B = int(rs.randint(1, 10))
+    N = int(rs.choice([37, 515, 2049, 4099, 9001, 20011]))
+    M = int(rs.randint(1, 3000))
+    S_ = int(rs.randint(1, min(N, 300) + 1))
+    x = S.uniform_cloud(seed, B, N)
+    if seed % 2:
+        x = S.lattice(x, 64)
+    xn = x.numpy()
+    start = S.fps_start(seed, B, N).numpy()
+    idx, new_xyz = run_fps(api, dev, xn, S_, start)
+    ref = oracle.farthest_point_sample(xn, S_, start)
+    assert np.array_equal(idx, ref)
+    radius = float(rs.uniform(0.05, 0.6))
+    nsample = int(rs.randint(1, min(N, 70) + 1))
+    g = api.enc.query_ball_point(radius, nsample, x.to(dev), torch.from_numpy(new_xyz).to(dev)).cpu().numpy()
+    assert np.array_equal(g, oracle.query_ball_point(radius, nsample, xn, new_xyz))
+    y = S.uniform_cloud(seed + 50, B, M)
+    if seed % 2:
+        y = S.lattice(y, 64)
+    r, ra, c, ca = api.ops.nn_min_pair_arg(x.to(dev), y.to(dev))
+    ref_r, ref_ra = oracle.nn_min(xn, y.numpy(), 0, want_arg=True)
+    ref_c, ref_ca = oracle.nn_min(y.numpy(), xn, 0, want_arg=True)
+    assert np.array_equal(bits(r.cpu().numpy()), bits(ref_r)) and np.array_equal(ra.cpu().numpy(), ref_ra)
+    assert np.array_equal(bits(c.cpu().numpy()), bits(ref_c)) and np.array_equal(ca.cpu().numpy(), ref_ca)
+    k = int(rs.randint(1, min(M, 16) + 1))
+    q = x[:, : min(N, 700)].contiguous()
+    d, i = api.ops.knn(q.to(dev), y.to(dev), k)
+    rd, ri = oracle.knn(q.numpy(), y.numpy(), k)
+    assert np.array_equal(d.cpu().numpy(), rd)
+    if seed % 2 == 0:  # on lattice clouds equal-distance neighbours make the index order implementation-defined
+        assert np.array_equal(i.cpu().numpy(), ri)
