@@ -1,0 +1,51 @@
+"""CPU, build container only: ``patch_reference()`` swaps the hot-path symbols inside an importable checkout of the
+reference and the drop-in modules keep the reference's parameter names (so its checkpoints load).  Skipped where the
+reference is not mounted (the GPU box)."""
+import importlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+REF = os.environ.get("PCST_REFERENCE", "/root/reference")
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference checkout not mounted")
+
+_SCRIPT = r"""
+import os, sys, tempfile, types
+sys.path.insert(0, {ref!r}); sys.path.insert(0, {repo!r})
+os.chdir(tempfile.mkdtemp())                      # config/config.py creates directories in the cwd
+import torch
+import models.pointnet2_encoder as ref_enc
+ref_keys = list(ref_enc.PointNet2Encoder(feature_dim=256).state_dict().keys())
+ref_shapes = [tuple(v.shape) for v in ref_enc.PointNet2Encoder(feature_dim=256).state_dict().values()]
+import pointcloud_style_transfer_b200 as pcst
+pcst.patch_reference()
+import models.diffusion_model as dm, models.losses as losses
+ours = ref_enc.PointNet2Encoder(feature_dim=256)
+assert type(ours).__module__.startswith("pointcloud_style_transfer_b200"), type(ours).__module__
+assert list(ours.state_dict().keys()) == ref_keys
+assert [tuple(v.shape) for v in ours.state_dict().values()] == ref_shapes
+se = dm.StyleEncoder(256)                         # the reference's own caller now builds the B200 encoder
+assert type(se.encoder).__module__.startswith("pointcloud_style_transfer_b200")
+for name in ("upsample_knn", "downsample", "_voxel_grid_downsample_torch"):
+    assert getattr(dm.HierarchicalProcessor, name).__module__.startswith("pointcloud_style_transfer_b200"), name
+assert losses.chamfer_distance_chunked_optimized.__module__.startswith("pointcloud_style_transfer_b200")
+assert losses.DiffusionLoss.__module__.startswith("pointcloud_style_transfer_b200")
+try:                                              # no CPU fallback: CPU tensors raise instead of computing
+    ours.eval()(torch.zeros(1, 64, 3))
+except RuntimeError as e:
+    assert "CUDA" in str(e)
+else:
+    raise AssertionError("CPU input did not raise")
+print("ok")
+"""
+
+
+def test_patch_reference_swaps_symbols_and_keeps_state_dict_keys():
+    out = subprocess.run([sys.executable, "-c", _SCRIPT.format(ref=REF, repo=REPO)], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().endswith("ok")
