@@ -287,7 +287,7 @@ static FpsPlan fps_plan(int B, int N) {
     int threads = tuning("fps.threads", 0);
     // measured (B200, 512 -> 128): 128 threads 63 us, 32 threads 72 us, 512 threads 65 us per launch
     if (threads == 0) threads = (C == 1 && N <= 64) ? 32 : ((C == 1 && N <= 2048) ? 128 : kFpsMaxThreads);
-    if (threads != 32 && threads != 128) threads = kFpsMaxThreads;
+    if (threads != 32 && threads != 64 && threads != 128 && threads != 256) threads = kFpsMaxThreads;
     p.threads = threads;
     const long lanes = (long)threads * C;                 // threads that share one cloud
     const long per_thread = (N + lanes - 1) / lanes;

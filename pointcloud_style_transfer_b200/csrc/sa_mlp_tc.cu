@@ -480,7 +480,9 @@ struct TcPlan {
 };
 
 // C = CTAs per row tile (N split over a cluster): every step computes n / C channels per CTA.
-static TcPlan tc_plan(int D, const int* cout, int C) {
+// dense = many more row tiles than SMs: a small weight ring (2 stages of 8 KiB) so that 2-4 CTAs share an SM and one
+// tile's epilogue overlaps another's MMAs; otherwise a deep ring for the latency of a single tile.
+static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false) {
     TcPlan p = {};
     p.ok = false;
     p.C = C;
@@ -519,8 +521,9 @@ static TcPlan tc_plan(int D, const int* cout, int C) {
     const int max_nc = n0c > n1c ? (n0c > n2c ? n0c : n2c) : (n1c > n2c ? n1c : n2c);
     // K rows per chunk of a step: as many as fit a ring stage (narrow per-CTA slices get long chunks, so that the
     // number of dependent TMA round trips stays small)
-    auto chunk_rows = [](int kp, int nc) {
-        int ck = kTcStageBytes / (nc * 2) / 16 * 16;
+    const int stage_target = dense ? kTcStageBytes / 2 : kTcStageBytes;
+    auto chunk_rows = [stage_target](int kp, int nc) {
+        int ck = stage_target / (nc * 2) / 16 * 16;
         if (ck < 16) ck = 16;
         return ck < kp ? ck : kp;
     };
@@ -541,7 +544,7 @@ static TcPlan tc_plan(int D, const int* cout, int C) {
     const uint32_t limit = 225 * 1024;
     auto nchunks = [&](int kp, int nc) { const int ck = chunk_rows(kp, nc); return (kp + ck - 1) / ck; };
     int total_chunks = nchunks(p.kp0, n0c) + h2 * h1 * (nchunks(n0, n1c) + nchunks(n1h, n2c));
-    p.nstages = kTcMaxStages;
+    p.nstages = dense ? 2 : kTcMaxStages;
     while (p.nstages > 2 && (fixed + p.nstages * p.stage_bytes > limit || (int)p.nstages > total_chunks)) --p.nstages;
     if (fixed + p.nstages * p.stage_bytes > limit) return p;
     p.off_ring = 0;
@@ -619,12 +622,12 @@ int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, int C, void* blob, cudaStream_
 
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
                   int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream) {
-    const TcPlan p = tc_plan(D, cout, C);
+    const size_t rows_sz = (size_t)B * S * K;
+    const TcPlan p = tc_plan(D, cout, C, /*dense=*/(rows_sz + kTcM - 1) / kTcM > (size_t)2 * kNumSMs);
     if (!p.ok) {
         set_error("sa_mlp_max (tensor-core path): unsupported layer widths / cluster size");
         return PCST_ERR_UNSUPPORTED;
     }
-    const size_t rows_sz = (size_t)B * S * K;
     if (rows_sz >= (1u << 30)) {
         set_error("sa_mlp_max: B*S*K too large");
         return PCST_ERR_INVALID;

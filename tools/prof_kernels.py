@@ -37,6 +37,14 @@ if "fpsprobe" in which:
         _lib.set_tuning("fps.prune", mode)
         timeit(f"fps 120k->512 probe [{label}]", lambda: ops.fps(x, 512, start), reps=10)
     _lib.set_tuning("fps.prune", 0)
+if "fps2nd" in which:
+    from pointcloud_style_transfer_b200 import _lib
+    x512 = S.lidar_scan(0, 512).to(dev)
+    _, c512 = ops.fps(x, 512, start)          # the real stage-2 input: the 512 centroids of a 120k scan
+    for t in (32, 64, 128, 256, 512):
+        _lib.set_tuning("fps.threads", t)
+        timeit(f"fps 512->128 (stage-1 centroids) threads={t}", lambda: ops.fps(c512, 128, start * 0), reps=20)
+    _lib.set_tuning("fps.threads", 0)
 if "fps" in which:
     from pointcloud_style_transfer_b200 import _lib
     timeit("fps 120k->512 (lidar order)", lambda: ops.fps(x, 512, start))
