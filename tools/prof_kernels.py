@@ -79,6 +79,16 @@ if "fps" in which:
     timeit("fps 4x16384->512", lambda: ops.fps(x16, 512, st4))
     x512 = S.uniform_cloud(0, 1, 512).to(dev)
     timeit("fps 512->128", lambda: ops.fps(x512, 128, start * 0))
+if "ballbatch" in which:
+    xb = torch.cat([S.lidar_scan(i, 16384) for i in range(32)], 0).to(dev)
+    st = torch.zeros(32, dtype=torch.long, device=dev)
+    _, c1 = ops.fps(xb, 512, st)
+    timeit("ball_query 32 x (512 x 16384) r=0.2 ns=32", lambda: ops.ball_query(xb, c1, 0.04, 32))
+    _, c2 = ops.fps(c1, 128, st)
+    timeit("ball_query 32 x (128 x 512) r=0.4 ns=64 [bq_small]", lambda: ops.ball_query(c1, c2, 0.16, 64))
+    timeit("ball_query 1 x (128 x 512) r=0.4 ns=64 [bq_small]", lambda: ops.ball_query(c1[:1].contiguous(), c2[:1].contiguous(), 0.16, 64))
+    timeit("fps 32 x 16384 -> 512", lambda: ops.fps(xb, 512, st))
+    timeit("fps 32 x 512 -> 128", lambda: ops.fps(c1, 128, st))
 if "ball" in which:
     _, c1 = ops.fps(x, 512, start)
     timeit("ball_query 512x120k r=0.2 ns=32", lambda: ops.ball_query(x, c1, 0.04, 32))
