@@ -265,6 +265,21 @@ def main():
         ms_ch = timed(lambda: chamfer_distance_chunked_optimized(x_dev, y_dev), max(1, args.chamfer_steps))
     ch_ms = max(statistics.mean(ms_ch), 1e-9)
 
+    # ---- FP32-pipe peak measured in the same run (packed FMA chains on every SM), for the Chamfer roofline ----
+    from pointcloud_style_transfer_b200 import _lib
+    import ctypes as _ct
+    scratch = torch.zeros(1, device=dev)
+    probe = lambda: _lib.load().pcst_fp32_probe(20000, _ct.c_void_p(scratch.data_ptr()),
+                                                _ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+    probe()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    probe_flop = probe()
+    ev1.record()
+    torch.cuda.synchronize()
+    fp32_measured = probe_flop / (ev0.elapsed_time(ev1) * 1e-3) / 1e12 if probe_flop else None
+
     # ---- batched throughput: 8 scans per GPU in one graph (FPS = 8 concurrent 16-CTA clusters, one per GPC) ----
     batched = None
     if args.batched_scans < 0:  # auto: as many scans as the FPS clusters that fit the GPU at once
@@ -280,7 +295,7 @@ def main():
 
     # ---- N > 1: ONE 120k x 120k Chamfer with the query points sharded over the ranks (BASELINE config 5):
     # all-gather of the target cloud + one sweep of the local [N/G x M] tile + MIN all-reduce of the column minima
-    ch_sharded = None
+    ch_sharded = knn_sharded = None
     if world > 1:
         from pointcloud_style_transfer_b200 import distributed as D
         p_full, t_full = S.lidar_scan(0), S.lidar_scan(100)
@@ -293,6 +308,12 @@ def main():
                           max(1, args.chamfer_steps))
             cd_one = chamfer_distance_chunked_optimized(p_full.to(dev), t_full.to(dev))
         ch_sharded = (statistics.mean(ms_sh), float((cd_sh - cd_one).abs().max() / cd_one.abs().max()))
+        # the kNN sweep of the same configuration: this rank's slice of the queries against ALL reference points
+        with torch.no_grad():
+            for _ in range(2):
+                D.knn_query_sharded(p_loc, t_loc, 3)
+            ms_knn = timed(lambda: D.knn_query_sharded(p_loc, t_loc, 3), max(1, args.chamfer_steps))
+        knn_sharded = statistics.mean(ms_knn)
 
     def allmax(v):
         if world == 1:
@@ -307,6 +328,7 @@ def main():
     fps_ms_max = allmax(fps_ms)
     t_b = allmax(batched) if batched is not None else None
     t_sh = allmax(ch_sharded[0]) if ch_sharded is not None else None
+    t_knn = allmax(knn_sharded) if knn_sharded is not None else None
 
     if rank == 0:
         value = world * N_POINTS / (t_dev * 1e-3)
@@ -314,7 +336,8 @@ def main():
         fps_bytes = NPOINT1 * N_POINTS * 20.0           # streaming-model bytes, SURVEY.md §8(d)
         fps_gbs = fps_bytes / (fps_ms_max * 1e-3) / 1e9
         pairs = 2.0 * N_POINTS * N_POINTS               # both directions, as the reference evaluates them
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s, FP32 CUDA cores
+        fp32_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s, FP32 CUDA cores at the max SM clock
+        fp32_peak = fp32_measured or fp32_nominal
         # one sweep serves both directions (the second matrix is the exact transpose): N*M unique pair evaluations
         ch_tflops = 8.0 * (pairs / 2) / (t_ch * 1e-3) / 1e12
         line = {
@@ -342,7 +365,9 @@ def main():
                         "roofline": {"kernel": "nn_min_pair_kernel<0>", "bound": "fp32", "achieved": ch_tflops, "peak": fp32_peak,
                                      "unit": "TFLOP/s", "frac": ch_tflops / fp32_peak,
                                      "model": "8 flop per UNIQUE pair evaluation (N*M: one sweep yields both directions' minima); "
-                                              "peak = 148 SMs x 128 lanes x 2 x sm_max_mhz (computed, not measured)",
+                                              "peak = packed-FMA micro-benchmark timed in this run (pcst_fp32_probe); nominal "
+                                              "148 SMs x 128 lanes x 2 x sm_max_mhz = %.1f" % fp32_nominal,
+                                     "peak_source": "measured in this run" if fp32_measured else "computed",
                                      "frac_if_both_directions_counted": 2 * ch_tflops / fp32_peak}},
             "clocks": clocks,
         }
@@ -356,6 +381,10 @@ def main():
                 "value": pairs / (t_sh * 1e-3), "unit": "pairs/s", "ms_per_call": t_sh, "scaling": "strong",
                 "collectives": "all-gather target (1.44 MB), all-reduce MIN of 120k column minima, all-reduce SUM of row sums",
                 "rel_diff_vs_single_gpu": ch_sharded[1]}
+            line["knn_query_sharded"] = {
+                "metric": "3-NN search, 120k queries x 120k references, queries sharded over %d GPUs (fp64-exact ranking)" % world,
+                "value": N_POINTS * float(N_POINTS) / (t_knn * 1e-3), "unit": "pairs/s", "ms_per_call": t_knn,
+                "scaling": "strong", "collectives": "all-gather of the reference cloud (1.44 MB); results stay sharded"}
         if not args.no_cpu_baseline and world == 1:
             times, cores = cpu_encoder_baseline(budget_s=10.0)
             line["cpu_baseline"] = {"value": N_POINTS / statistics.mean(times), "unit": "points/s", "cores": cores,

@@ -56,6 +56,11 @@ int pcst_get_tuning(const char* key, int* value);
  * stream while the first FPS runs on 16 of the 148 SMs; no reference counterpart (a scheduling aid, not arithmetic). */
 int pcst_l2_prefetch(const void* ptr, size_t bytes, pcst_stream_t stream);
 
+/* FP32-pipe calibration for the roofline of the distance kernels: launches independent packed-FMA chains on every SM
+ * and returns the number of flop the launch performs (0 on error); the caller times it with CUDA events.
+ * scratch: one float of device memory (never written in practice). */
+long long pcst_fp32_probe(int iters, float* scratch, pcst_stream_t stream);
+
 /* ---- farthest_point_sample: models/pointnet2_encoder.py:30-45 --------------------------------
  * xyz [B,N,3]; start [B] = the start index per cloud (the reference draws it with torch.randint
  * on the CPU generator, :36 -- that draw stays in the caller); out [B,npoint] int64.

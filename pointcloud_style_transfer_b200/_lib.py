@@ -36,6 +36,7 @@ SIGNATURES = {
     "pcst_device_check": (c_int, []),
     "pcst_set_tuning": (c_int, [c_char_p, c_int]),
     "pcst_get_tuning": (c_int, [c_char_p, POINTER(c_int)]),
+    "pcst_fp32_probe": (ctypes.c_longlong, [c_int, c_void_p, c_void_p]),
     "pcst_l2_prefetch": (c_int, [c_void_p, c_size_t, c_void_p]),
     "pcst_fps_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_fps_max_concurrent_clouds": (c_int, [c_int]),

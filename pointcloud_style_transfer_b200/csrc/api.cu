@@ -71,6 +71,23 @@ __global__ void l2_prefetch_kernel(const unsigned char* __restrict__ p, size_t b
     if (line < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + line));
 }
 
+// ---- FP32 pipe calibration: independent packed FMA chains, 2 * 2 * 8 * iters flop per thread -----------------
+__global__ void __launch_bounds__(256)
+fp32_probe_kernel(int iters, float* __restrict__ out) {
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(1.0f + threadIdx.x * 1e-6f + i, 0.5f + i);
+    const float2 m = make_float2(0.999999f, 1.000001f), c = make_float2(1e-7f, -1e-7f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(a[i], m, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+    if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
+}
+
 int launch_pack(const float* xyz, int B, int N, int Npad, float4* out, cudaStream_t stream) {
     int blocks = (Npad + 255) / 256;
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
@@ -107,6 +124,14 @@ int pcst_l2_prefetch(const void* ptr, size_t bytes, pcst_stream_t stream_) {
     const unsigned blocks = (unsigned)((lines + 255) / 256);
     pcst::l2_prefetch_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>((const unsigned char*)ptr, bytes);
     return pcst::check_cuda(cudaGetLastError(), "l2_prefetch_kernel");
+}
+
+long long pcst_fp32_probe(int iters, float* scratch, pcst_stream_t stream_) {
+    if (iters <= 0 || !scratch) return 0;
+    const int blocks = 8 * pcst::kNumSMs, threads = 256;
+    pcst::fp32_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream_>>>(iters, scratch);
+    if (cudaGetLastError() != cudaSuccess) return 0;
+    return (long long)blocks * threads * 8 * 2 * 2 * iters;  // 8 chains x 2 lanes x (mul + add) per iteration
 }
 
 int pcst_set_tuning(const char* key, int value) {
