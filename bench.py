@@ -40,13 +40,18 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML.  Started before the warm-up (NVML initialisation takes
+    longer than a short timed region); only samples taken between begin() and end() -- the timed region -- count."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.max_mhz, self.error = [], None, None   # samples: (time, sm_mhz, reason bits)
+        self.t0 = self.t1 = None
+        self.ready = threading.Event()
         self._stop_evt = threading.Event()
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def run(self):
         try:
@@ -54,30 +59,36 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-            }
+            self.ready.set()
             while not self._stop_evt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), r))
                 time.sleep(self.period)
         except Exception as e:  # NVML missing: report that instead of inventing numbers
-            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.error = f"nvml_unavailable:{type(e).__name__}"
+            self.ready.set()
+
+    def begin(self):
+        self.ready.wait(timeout=10)
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= (self.t1 or float("inf"))]
+        reasons = set()
+        for _, _, r in inside:
+            reasons |= {name for bit, name in self.NAMES.items() if r & bit}
+        if self.error:
+            reasons.add(self.error)
+        return {"sm_mhz": statistics.median(m for _, m, _ in inside) if inside else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(inside)}
 
 
 def cpu_encoder_baseline(budget_s: float, scan_seed: int = 0):
@@ -203,6 +214,8 @@ def main():
     genc = GraphedEncoder(enc)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     torch.manual_seed(1234 + rank)
     for _ in range(W):
         genc(x_dev)
@@ -219,9 +232,8 @@ def main():
         barrier()
         return [a.elapsed_time(b) for a, b in evs]
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ops.launch_count
+    sampler.begin()
 
     # ---- device-resident: input already in HBM, one graph replay per step ----
     ms_dev = timed(lambda: genc(x_dev), K)
@@ -238,6 +250,7 @@ def main():
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, K)
+    sampler.end()
     clocks = sampler.stop()
 
     # ---- per-op durations (eager, CUDA events around each C-ABI call), for the roofline ----

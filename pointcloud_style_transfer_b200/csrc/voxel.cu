@@ -133,7 +133,8 @@ vox_scatter_kernel(const unsigned int* __restrict__ kin, const unsigned int* __r
     unsigned int total = 0, before = 0;
     {
         const unsigned int* g = ghist + ((size_t)b * 256 + tid) * ntiles;
-        for (int c = 0; c < ntiles; ++c) {
+#pragma unroll 8
+        for (int c = 0; c < ntiles; ++c) {  // independent loads: keep several in flight
             const unsigned int h = g[c];
             before += c < tile ? h : 0u;
             total += h;
@@ -229,6 +230,7 @@ vox_runs_kernel(const unsigned int* __restrict__ keys, const unsigned int* __res
     const unsigned int* k = keys + (size_t)b * N;
     const unsigned int* v = vals + (size_t)b * N;
     unsigned int before = 0, total = 0;
+#pragma unroll 8
     for (int c = 0; c < ntiles; ++c) {
         const unsigned int h = gcount[(size_t)b * ntiles + c];
         before += c < tile ? h : 0u;
