@@ -34,6 +34,7 @@ static std::map<std::string, int>& tune_map() {
         {"fps.threads", 0},           // 0 = auto (32, 128 or 512 threads per CTA)
         {"fps.prune", 0},             // 0/1 = bounding-box skip test on, 2 = off
         {"sa_mlp.variant", 0},
+        {"sa_mlp.pdl", 0},            // 0/1 = programmatic dependent launch of the tcgen05 MLP kernel on, 2 = off
     };
     return m;
 }

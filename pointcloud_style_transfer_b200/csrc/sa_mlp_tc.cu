@@ -170,6 +170,10 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     const uint32_t C = a.cluster;
     const uint32_t rank = C > 1 ? cluster_ctarank() : 0;
     const int row0 = (int)(blockIdx.x / C) * kTcM;
+    // Programmatic dependent launch: let the next kernel of the stream start its own prologue now; this kernel's
+    // prologue (barriers, TMEM, cluster rendezvous, the first weight chunks, the scale/shift tables -- nothing the
+    // previous kernel produces) runs before griddepcontrol.wait, the gather of the previous kernel's output after it.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (tid == 0) {
         for (int s = 0; s < kTcMaxStages; ++s) {
@@ -267,6 +271,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
             const float* src = reinterpret_cast<const float*>(a.blob + a.ss_blob_off);
             for (int c = tid; c < 2 * a.total_ch; c += kTcEpiThreads) ss[c] = src[c];
         }
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous kernel's output (idx, feats, xyz) is complete
         {
             // Layer-0 operand, one thread per row: operand row k = feature channel k (k < D), then the three
             // relative coordinates, then zero padding up to kp0.  Features are read with 16 independent 128-bit
@@ -653,13 +658,15 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = p.smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = tuning("sa_mlp.pdl", 1) == 1 ? 2 : 1;  // 2 = off (A/B measurements)
     PCST_CUDA(cudaLaunchKernelEx(&cfg, sa_mlp_tc_kernel, a));
     return PCST_OK;
 }

@@ -246,8 +246,10 @@ class PointNet2Encoder(nn.Module):
             for t in (l2_xyz, idx2):  # allocated on the side stream, consumed on the main stream
                 t.record_stream(main)
         l2_points = self.sa2._mlp_fused(l1_xyz, l1_points.permute(0, 2, 1), l2_xyz, idx2)   # [B,256,128]
-        _, global_feature = self.sa3(l2_xyz, l2_points.permute(0, 2, 1))
-        return global_feature.view(B, -1)
+        # group_all stage without materialising its all-zero new_xyz (:82), which nothing downstream reads
+        packed, couts, cluster = self.sa3._packed_params(B, 1, l2_xyz.shape[1])
+        g = ops.sa_mlp_max(l2_xyz, l2_points.permute(0, 2, 1), None, None, packed, couts, self.sa3.mlp_precision, cluster)
+        return g[:, 0, :self.sa3.mlp_convs[-1].out_channels].reshape(B, -1)
 
     def set_mlp_precision(self, precision: int) -> "PointNet2Encoder":
         """0 = fp32 CUDA cores (parity within rtol 1e-4), 1 = bf16 tcgen05 tensor cores (rtol 2e-2)."""
