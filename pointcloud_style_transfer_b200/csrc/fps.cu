@@ -57,7 +57,9 @@ __device__ __forceinline__ float box_gap(float lo, float hi, float c) {
 // P > 0: register-resident, P points per thread (P even), blockDim.x in {32, 128, 512}.
 // P == 0: streaming fallback for clouds that do not fit the register file of one cluster: distances
 // live in a global workspace and the points are re-read (from L2) every iteration.
-template <int P>
+// PROBE = true compiles the latency probes selected by `prune` >= 3 (fps.prune tuning knob, invalid results); the
+// production instantiation does not carry their predicates on its per-iteration path.
+template <int P, bool PROBE>
 __global__ void __launch_bounds__(kFpsMaxThreads, 1)
 fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __restrict__ start,
            int64_t* __restrict__ out, float* __restrict__ new_xyz, int pts_per_cta, float* __restrict__ dist_ws,
@@ -151,9 +153,17 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         unsigned widx;
         if (P > 0) {
             // ---- exact skip test (warp-uniform) ----
-            const float gx = box_gap(lox, hix, cx), gy = box_gap(loy, hiy, cy), gz = box_gap(loz, hiz, cz);
-            const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-            if ((prune && lb >= __int_as_float(cmax)) || (prune >= 3 && it > 0)) {
+            // (x and y together as one packed fp32x2 sequence; every lane operation is the same RN add / multiply)
+            const float2 c2 = make_float2(cx, cy);
+            const float2 ga = __fadd2_rn(make_float2(lox, loy), make_float2(-c2.x, -c2.y));
+            const float2 gb = __fadd2_rn(c2, make_float2(-hix, -hiy));
+            const float2 g2 = make_float2(fmaxf(fmaxf(ga.x, gb.x), 0.0f), fmaxf(fmaxf(ga.y, gb.y), 0.0f));
+            const float gz = box_gap(loz, hiz, cz);
+            const float2 sq = __fmul2_rn(g2, g2);
+            const float lb = __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(gz, gz));
+            bool skip = prune && lb >= __int_as_float(cmax);
+            if (PROBE) skip = skip || (prune >= 3 && it > 0);
+            if (skip) {
                 wmax = cmax;
                 widx = cidx;
             } else {
@@ -196,7 +206,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         // ---- block argmax, computed redundantly by every warp ----
         int bmax = wmax;
         unsigned bidx = widx;
-        if (nwarps > 1 && prune != 4) {
+        if (nwarps > 1 && !(PROBE && prune == 4)) {
             if (lane == 0) sh.wslot[par][warp] = make_int2(wmax, (int)widx);
             __syncthreads();
             int2 e = lane < nwarps ? sh.wslot[par][lane] : make_int2((int)0x80000000, (int)kNoIdx);
@@ -206,7 +216,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, const int64_t* __re
         // shared-memory slot of the block's best point (P > 0)
         const int bslot = P > 0 ? (int)((bidx / CH) >> log2c) * CH + (int)(bidx % CH) : 0;
 
-        if (C == 1 || prune == 5) {
+        if (C == 1 || (PROBE && prune == 5)) {
             far = bidx;
             if (P > 0) {
                 const float4 q4 = smem_pts[bslot];
@@ -305,7 +315,9 @@ static FpsPlan fps_plan(int B, int N) {
 template <int P>
 static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoint, const int64_t* start,
                       int64_t* out, float* new_xyz, float* dist_ws, cudaStream_t stream) {
-    auto kern = fps_kernel<P>;
+    int prune = tuning("fps.prune", 1);
+    prune = prune == 2 ? 0 : prune;
+    auto kern = prune >= 3 ? fps_kernel<P, true> : fps_kernel<P, false>;
     if (p.smem > 32 * 1024)  // dynamic + static (FpsShared) must stay under the opt-in limit, not the 48 KiB default
         PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     if (p.C > 8) PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -325,8 +337,6 @@ static int fps_launch(const FpsPlan& p, const float* xyz, int B, int N, int npoi
     // 2 = off (for A/B measurements); 3 = skip every chunk after the first iteration (WRONG results:
     // measures the latency floor of the exchange chain alone); 4 = 3 without the block-level reduction;
     // 5 = 3 without the cluster exchange (latency probes, results invalid)
-    int prune = tuning("fps.prune", 1);
-    prune = prune == 2 ? 0 : prune;
     int log2c = 0;
     while ((1 << log2c) < p.C) ++log2c;
     PCST_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, start, out, new_xyz, pts_per_cta, dist_ws, prune, log2c));
@@ -348,7 +358,7 @@ extern "C" size_t pcst_fps_workspace_bytes(int B, int N, int npoint) {
 // 16-CTA clusters (148 SMs do not hold nine, and not every GPC holds one).
 template <int P>
 static int fps_max_clusters(const FpsPlan& p) {
-    auto kern = fps_kernel<P>;
+    auto kern = fps_kernel<P, false>;
     if (p.smem > 32 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
         return 0;
