@@ -26,7 +26,8 @@ constexpr int kKnnMaxK = 16;
 template <int KMAX>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q, int R, int k,
-           int64_t* __restrict__ idx, double* __restrict__ dist) {
+           int64_t* __restrict__ idx, double* __restrict__ dist, int splits, int tiles_per_split,
+           double* __restrict__ part_d, int* __restrict__ part_i) {
     // reference points of the tile as pairs of consecutive candidates per component, so that one packed
     // FADD2 / FMUL2 / FFMA2 sequence prefilters two candidates against the thread's query
     // (KMAX <= 4) or as float4 rows, one broadcast LDS.128 per candidate (longer lists)
@@ -74,8 +75,11 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q
         }
     };
 
-    for (int j0 = 0; j0 < R; j0 += kKnnTile) {
-        const int n = R - j0 < kKnnTile ? R - j0 : kKnnTile;
+    // blockIdx.z = slice of the reference range (few queries: the scan is split so that the launch fills the GPU)
+    const int jbegin = blockIdx.z * tiles_per_split * kKnnTile;
+    const int jend = min(R, jbegin + tiles_per_split * kKnnTile);
+    for (int j0 = jbegin; j0 < jend; j0 += kKnnTile) {
+        const int n = jend - j0 < kKnnTile ? jend - j0 : kKnnTile;
         __syncthreads();
         for (int t = threadIdx.x; t < kKnnTile; t += kKnnThreads) {
             // slots beyond the cloud hold +inf coordinates: their distance is +inf (or NaN) and never passes `<=`
@@ -125,9 +129,50 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q
 #pragma unroll
             for (int u = 0; u < KMAX; ++u)
                 if (u == t) { v = bd[u]; j = bi[u]; }
-            idx[((size_t)b * Q + q) * k + t] = j;
-            dist[((size_t)b * Q + q) * k + t] = __dsqrt_rn(v);
+            if (splits == 1) {
+                idx[((size_t)b * Q + q) * k + t] = j;
+                dist[((size_t)b * Q + q) * k + t] = __dsqrt_rn(v);
+            } else {  // squared distances of this slice's k best; merged by knn_merge_kernel
+                const size_t o = (((size_t)b * Q + q) * splits + blockIdx.z) * k + t;
+                part_d[o] = v;
+                part_i[o] = j;
+            }
         }
+    }
+}
+
+// k best of `splits` sorted partial lists per query.  Slices cover ascending reference ranges and each list is sorted
+// with ties in index order, so inserting them slice by slice with a strict `<` keeps the lowest index among equals.
+__global__ void knn_merge_kernel(const double* __restrict__ part_d, const int* __restrict__ part_i, long total, int splits,
+                                 int k, int64_t* __restrict__ idx, double* __restrict__ dist) {
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    double bd[kKnnMaxK];
+    int bi[kKnnMaxK];
+    for (int t = 0; t < k; ++t) {
+        bd[t] = __longlong_as_double(0x7ff0000000000000ll);
+        bi[t] = 0;
+    }
+    const double* pd = part_d + (size_t)q * splits * k;
+    const int* pi = part_i + (size_t)q * splits * k;
+    for (int e = 0; e < splits * k; ++e) {
+        double cd = pd[e];
+        int ci = pi[e];
+        if (!(cd < bd[k - 1])) continue;
+        for (int u = 0; u < k; ++u) {
+            if (cd < bd[u]) {
+                const double td = bd[u];
+                const int ti = bi[u];
+                bd[u] = cd;
+                bi[u] = ci;
+                cd = td;
+                ci = ti;
+            }
+        }
+    }
+    for (int t = 0; t < k; ++t) {
+        idx[(size_t)q * k + t] = bi[t];
+        dist[(size_t)q * k + t] = __dsqrt_rn(bd[t]);
     }
 }
 
@@ -162,24 +207,60 @@ __global__ void knn_interpolate_kernel(const float* __restrict__ feat, const int
 
 using namespace pcst;
 
+// reference-range slices: 1 when the queries alone fill the GPU, more when they do not
+static int knn_splits(int B, int Q, int R) {
+    const long ctas = (long)B * ((Q + kKnnThreads - 1) / kKnnThreads);
+    const int tiles = (R + kKnnTile - 1) / kKnnTile;
+    long s = (2L * kNumSMs + ctas - 1) / ctas;
+    if (s > tiles) s = tiles;
+    if (s > 64) s = 64;
+    return s < 1 ? 1 : (int)s;
+}
+
 extern "C" size_t pcst_knn_workspace_bytes(int B, int Q, int R, int k) {
-    (void)B; (void)Q; (void)R; (void)k;
-    return 0;
+    if (B <= 0 || Q <= 0 || R <= 0 || k <= 0) return 0;
+    const int s = knn_splits(B, Q, R);
+    if (s == 1) return 0;
+    return align_up((size_t)B * Q * s * k * sizeof(double), 256) + align_up((size_t)B * Q * s * k * sizeof(int), 256);
 }
 
 extern "C" int pcst_knn_f32(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx,
                             double* dist, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
-    (void)ws; (void)ws_bytes;
     cudaStream_t stream = (cudaStream_t)stream_;
     PCST_CHECK_ARG(query && ref && idx && dist, "null pointer");
     PCST_CHECK_ARG(B > 0 && Q > 0 && R > 0, "B, Q, R must be positive");
+    PCST_CHECK_ARG(B <= 65535, "B must be <= 65535");
     PCST_CHECK_ARG(k >= 1 && k <= kKnnMaxK && k <= R, "k must be in [1, min(16, R)]");
-    dim3 grid((Q + kKnnThreads - 1) / kKnnThreads, B);
-    if (k <= 1) knn_kernel<1><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist);
-    else if (k <= 4) knn_kernel<4><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist);
-    else if (k <= 9) knn_kernel<9><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist);
-    else knn_kernel<16><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist);
-    return check_cuda(cudaGetLastError(), "knn_kernel");
+    int splits = knn_splits(B, Q, R);
+    const int tiles = (R + kKnnTile - 1) / kKnnTile;
+    const int tps = (tiles + splits - 1) / splits;
+    splits = (tiles + tps - 1) / tps;  // no empty slice
+    // a slice must hold at least k points so that every partial list is full (the last slice may be shorter)
+    while (splits > 1 && (R - (splits - 1) * tps * kKnnTile) < k) splits = 1;
+    const size_t need = pcst_knn_workspace_bytes(B, Q, R, k);
+    double* part_d = nullptr;
+    int* part_i = nullptr;
+    if (splits > 1) {
+        if (!ws || ws_bytes < need || ((uintptr_t)ws & 255)) {
+            set_error("pcst_knn_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need);
+            return PCST_ERR_WORKSPACE;
+        }
+        part_d = (double*)ws;
+        part_i = (int*)((char*)ws + align_up((size_t)B * Q * knn_splits(B, Q, R) * k * sizeof(double), 256));
+    }
+    const int tps_arg = splits > 1 ? tps : tiles;
+    dim3 grid((Q + kKnnThreads - 1) / kKnnThreads, B, splits);
+    if (k <= 1) knn_kernel<1><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i);
+    else if (k <= 4) knn_kernel<4><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i);
+    else if (k <= 9) knn_kernel<9><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i);
+    else knn_kernel<16><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i);
+    PCST_CUDA(cudaGetLastError());
+    if (splits > 1) {
+        const long total = (long)B * Q;
+        knn_merge_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(part_d, part_i, total, splits, k, idx, dist);
+        PCST_CUDA(cudaGetLastError());
+    }
+    return PCST_OK;
 }
 
 extern "C" int pcst_knn_interpolate_f32(const float* feat, const int64_t* idx, const double* dist, int B, int R,
