@@ -13,6 +13,13 @@
 // warp).  The grid is (row tiles) x (candidate splits) x B; partial minima of the splits are merged
 // with atomicMin on the IEEE bits (all values are >= +0 after the clamp), or on a 64-bit
 // (bits << 32 | index) key when the argmin is requested, which also yields the lowest-index tie-break.
+//
+// Kernels in this file:
+//   nn_min_kernel<FORM,R,ARG,VEC2>   one direction (row minima), optionally with the argmin;
+//   nn_min_pair_kernel<FORM>          BOTH directions from one sweep: every pair evaluated once, row minima in
+//                                     registers, column minima by FMNMX3 tree + REDUX + per-warp strips;
+//   nn_min_pair_arg_kernel            the same sweep plus both argmins (block tracking + exact fix-up kernels);
+//   chamfer_bwd_kernel                gradient scatter of the Chamfer loss.
 #include "common.cuh"
 
 namespace pcst {
