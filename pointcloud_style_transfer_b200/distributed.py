@@ -45,6 +45,11 @@ def all_gather_ragged(x: torch.Tensor, group=None, total: Optional[int] = None) 
         sizes = [torch.zeros_like(n) for _ in range(world)]
         dist.all_gather(sizes, n, group=group)
         sizes = [int(s.item()) for s in sizes]
+    if min(sizes) == max(sizes):  # equal shards: one collective into one buffer, no padding, no per-rank slicing
+        buf = x.new_empty(world * x.shape[0], x.shape[1], x.shape[2])   # ranks concatenated along dim 0
+        dist.all_gather_into_tensor(buf, x.contiguous(), group=group)
+        buf = buf.view(world, x.shape[0], x.shape[1], x.shape[2])
+        return buf.permute(1, 0, 2, 3).reshape(x.shape[0], world * x.shape[1], x.shape[2])
     nmax = max(sizes)
     pad = x.new_zeros(x.shape[0], nmax, x.shape[2])
     pad[:, : x.shape[1]] = x

@@ -55,6 +55,9 @@ def _worker(rank, world, port, q):
         # a rank with an EMPTY query slice (more ranks than points would do this): rank 1 holds no pred points
         elo, ehi = (0, 5) if rank == 0 else (5, 5)
         cde = D.chamfer_query_sharded_one_sweep(pred[:, :5][:, elo:ehi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair)
+        even = S.uniform_cloud(9, 3, 64)                       # equal shards take the single-buffer all-gather
+        elo, ehi = D.slice_of_rank(64, world, rank)
+        ok_gather = ok_gather and torch.equal(D.all_gather_ragged(even[:, elo:ehi].contiguous(), total=64), even)
         scans = S.uniform_cloud(5, 5, 64)
         feats = D.encode_scans_sharded(_ToyEncoder(), scans)
         q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy(), cd1.numpy(), cdm1.numpy(), cde.numpy()))
