@@ -371,12 +371,12 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                         uint32_t packed[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float y0 = __fmaf_rn(__uint_as_float(r[h][2 * i]), sc[cb + 2 * i], sh[cb + 2 * i]);
-                            float y1 = __fmaf_rn(__uint_as_float(r[h][2 * i + 1]), sc[cb + 2 * i + 1], sh[cb + 2 * i + 1]);
-                            y0 = y0 > 0.f ? y0 : 0.f;
-                            y1 = y1 > 0.f ? y1 : 0.f;
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(y0, y1);
-                            packed[i] = *reinterpret_cast<uint32_t*>(&hh);
+                            // two channels per step: one packed FFMA2 for scale/shift, one cvt.rn.relu.bf16x2 for ReLU +
+                            // rounding + packing (upper half = second channel)
+                            const float2 s2 = *reinterpret_cast<const float2*>(&sc[cb + 2 * i]);
+                            const float2 t2 = *reinterpret_cast<const float2*>(&sh[cb + 2 * i]);
+                            const float2 y = __ffma2_rn(make_float2(__uint_as_float(r[h][2 * i]), __uint_as_float(r[h][2 * i + 1])), s2, t2);
+                            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(packed[i]) : "f"(y.y), "f"(y.x));
                         }
                         // channels cb..cb+7 and cb+8..cb+15 are two K chunks of the next operand
                         uint4* d0 = reinterpret_cast<uint4*>(outp + ((size_t)(cb >> 3) * kTcM + m) * 16);
