@@ -143,6 +143,10 @@ size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const 
 int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
                         int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision, int cluster,
                         const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream);
+/* Profiling aid (no reference counterpart): while `stamps` is non-NULL every tensor-core launch records, for each of its
+ * first `tiles` 128-row tiles, 16 uint64 in device memory: SM-clock stamps [0] tile start, [1] operand gathered, then per
+ * epilogue (accumulator ready, epilogue done); [15] = the SM id.  NULL switches it off. */
+void pcst_sa_mlp_set_probe(unsigned long long* stamps /*[tiles,16] device*/, int tiles);
 
 /* ---- nearest-neighbour minimum reduction ------------------------------------------------------
  * a [B,N,3], b [B,M,3] -> rowmin [B,N] = min_j D(a_i, b_j), rowarg [B,N] (optional, may be NULL) =

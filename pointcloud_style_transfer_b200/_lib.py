@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpcst.so")
+# PCST_LIB points at another build of the same C ABI (A/B timing of two builds on one box)
+LIB_PATH = os.environ.get("PCST_LIB") or os.path.join(_HERE, "csrc", "libpcst.so")
 
 PCST_OK = 0
 STATUS_NAMES = {0: "PCST_OK", -1: "PCST_ERR_INVALID", -2: "PCST_ERR_UNSUPPORTED", -3: "PCST_ERR_CUDA",
@@ -37,6 +38,7 @@ SIGNATURES = {
     "pcst_set_tuning": (c_int, [c_char_p, c_int]),
     "pcst_get_tuning": (c_int, [c_char_p, POINTER(c_int)]),
     "pcst_fp32_probe": (ctypes.c_longlong, [c_int, c_void_p, c_void_p]),
+    "pcst_sa_mlp_set_probe": (None, [c_void_p, c_int]),
     "pcst_l2_prefetch": (c_int, [c_void_p, c_size_t, c_void_p]),
     "pcst_fps_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_fps_max_concurrent_clouds": (c_int, [c_int]),

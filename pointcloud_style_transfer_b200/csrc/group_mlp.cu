@@ -157,6 +157,7 @@ size_t sa_mlp_tc_blob_bytes(int D, const int* cout, int C);
 int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, int C, void* blob, cudaStream_t stream);
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
                   int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream);
+void sa_mlp_tc_set_probe(unsigned long long* buf, int tiles);
 
 // fp32 blob: w0 [n0, 3+D] | w1 [n1, n0] | w2 [n2, n1] | scale0 shift0 scale1 shift1 scale2 shift2, each 256-byte aligned
 struct F32Blob {
@@ -237,7 +238,9 @@ extern "C" size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, in
     return align_up(rows * cout[0] * sizeof(float), 256) + align_up(rows * cout[1] * sizeof(float), 256);
 }
 
-extern "C" int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
+extern "C" void pcst_sa_mlp_set_probe(unsigned long long* stamps, int tiles) { pcst::sa_mlp_tc_set_probe(stamps, tiles); }
+
+int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
                                    int B, int N, int S, int K, int D, const int* cout, int precision, int cluster,
                                    const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

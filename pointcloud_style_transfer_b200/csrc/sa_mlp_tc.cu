@@ -31,6 +31,8 @@
 // the reference's fp32 result.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pcst {
@@ -74,6 +76,10 @@ struct TcArgs {
     float* out;                 // [B*S, cout] point-major
     int pool_atomic;            // 0: every group lies inside one tile (plain stores); 1: atomicMax merge
     uint32_t cluster;           // CTAs per row tile (N split); 1 = no cluster
+    unsigned long long* probe;  // profiling aid (pcst_sa_mlp_set_probe): [probe_tiles][16] SM-clock stamps per tile, or null
+    int probe_tiles;
+    int relaxed;                // throughput launch: the producer / MMA threads back off between barrier polls
+    int ntiles;                 // row tiles; a CTA (cluster) walks tiles first, first + stride, ... (persistent when > grid)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -128,7 +134,38 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The wait names the registers of the load it completes ("+r"): their uses cannot be scheduled above it, while a load
+// issued AFTER the wait into the other buffer stays in flight during the arithmetic on this one.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// Walk an accumulator's n columns 16 at a time with the NEXT 16 already loading: f(r, c0) per block.
+template <typename F>
+__device__ __forceinline__ void tmem_for_each16(uint32_t taddr, int n, F&& f) {
+    uint32_t ra[16], rb[16];
+    tmem_ld16_issue(taddr, ra);
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        tmem_ld_wait(ra);
+        const bool second = c0 + 16 < n;
+        if (second) tmem_ld16_issue(taddr + (uint32_t)c0 + 16u, rb);
+        f(ra, c0);
+        if (second) {
+            tmem_ld_wait(rb);
+            if (c0 + 32 < n) tmem_ld16_issue(taddr + (uint32_t)c0 + 32u, ra);
+            f(rb, c0 + 16);
+        }
+    }
+}
+// Poll with a pause: the single-lane producer / MMA warps share issue slots with two of the four epilogue warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, bool relaxed) {
+    while (!mbar_try_wait(bar, parity)) {
+        if (relaxed) __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // warps 0-3 only
 
 // ---- weight pre-pack: fp32 W[n0 + n, k0 + k] (row-major [Cout, Cin]) -> bf16 [kp/8][nlen][8], zero padded in K ----
@@ -156,7 +193,14 @@ __global__ void tc_pack_ss_kernel(const float* __restrict__ scale, const float* 
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads)
+// Two instantiations.  <168, true>: CTAs walk several row tiles when there are more tiles than the machine holds (two
+// CTAs per SM; barriers, TMEM and the scale/shift tables set up once, the weight ring streaming across tile boundaries).
+// <96, false>: one tile per CTA within the register budget that lets THREE CTAs share an SM.  A CTA's six warps land
+// 2/2/1/1 on the four SM partitions (16 Ki registers each), so three CTAs put five warps on a partition: 5 x 32 x 96
+// registers fit, 5 x 32 x 112 do not.  The narrow stages (SA1: 3 -> 64 -> 64 -> 128) are bound by the latency of a
+// tile's serial chain, so the third resident tile is worth more than the walk.
+template <int kMaxReg, bool kWalk>
+__global__ void __maxnreg__(kMaxReg)
 sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
@@ -169,7 +213,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t C = a.cluster;
     const uint32_t rank = C > 1 ? cluster_ctarank() : 0;
-    const int row0 = (int)(blockIdx.x / C) * kTcM;
+    const int tile_first = (int)(blockIdx.x / C), tile_stride = (int)(gridDim.x / C);
     // Programmatic dependent launch: let the next kernel of the stream start its own prologue now; this kernel's
     // prologue (barriers, TMEM, cluster rendezvous, the first weight chunks, the scale/shift tables -- nothing the
     // previous kernel produces) runs before griddepcontrol.wait, the gather of the previous kernel's output after it.
@@ -201,66 +245,74 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     if (warp == 4) {
         // ================= weight producer =================
         if (lane == 0) {
+            // the ring never drains between tiles: the next tile's first chunks load under this tile's epilogues
             uint32_t it = 0;
-            for (int s = 0; s < a.nsteps; ++s) {
-                const TcStep& st = a.st[s];
-                const unsigned char* src = a.blob + st.w_off + (size_t)rank * st.w_stride;
-                for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
-                    const uint32_t stage = it % a.nstages;
-                    if (it >= a.nstages) mbar_wait(&empty_bar[stage], ((it / a.nstages) - 1u) & 1u);
-                    const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
-                    const uint32_t bytes = (uint32_t)ck * st.n * 2u;
-                    mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                    tma_load_1d(smem + a.off_ring + stage * a.stage_bytes, src + (size_t)k0 * st.n * 2u, bytes,
-                                &full_bar[stage]);
+            for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles)
+                for (int s = 0; s < a.nsteps; ++s) {
+                    const TcStep& st = a.st[s];
+                    const unsigned char* src = a.blob + st.w_off + (size_t)rank * st.w_stride;
+                    for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
+                        const uint32_t stage = it % a.nstages;
+                        if (it >= a.nstages) mbar_wait_relaxed(&empty_bar[stage], ((it / a.nstages) - 1u) & 1u, kWalk && a.relaxed);
+                        const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
+                        const uint32_t bytes = (uint32_t)ck * st.n * 2u;
+                        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                        tma_load_1d(smem + a.off_ring + stage * a.stage_bytes, src + (size_t)k0 * st.n * 2u, bytes,
+                                    &full_bar[stage]);
+                    }
                 }
-            }
         }
     } else if (warp == 5) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t it = 0, seen = 0, need = 1;  // events on a_bar: the gather, then one per epilogue
+            // Events on a_bar, per tile: the gather, then one per epilogue EXCEPT the tile's last (pooled) one -- the
+            // next tile's gather event follows it in the same threads and stands for both (two arrivals nobody waits
+            // between would let the barrier run two phases ahead of this thread's parity wait).
+            uint32_t it = 0, seen = 0, need = 0;
             uint32_t xseen = 0;                   // operand-writing epilogues whose REMOTE slices have been awaited
-            int xstep = 0;                        // step scanned up to while counting those epilogues
-            for (int s = 0; s < a.nsteps; ++s) {
-                const TcStep& st = a.st[s];
-                while (seen < need) {
-                    mbar_wait(&a_bar, seen & 1u);
-                    ++seen;
-                }
-                if (C > 1) {
-                    // every operand-writing epilogue before this step: (C - 1) peers each push 128 x n x 2 bytes
-                    for (; xstep < s; ++xstep) {
-                        if (a.st[xstep].epi != 1) continue;
-                        uint64_t* xb = &x_bar[xseen & 1u];
-                        mbar_arrive_expect_tx(xb, (C - 1u) * (uint32_t)a.st[xstep].n * (kTcM * 2u));
-                        mbar_wait(xb, (xseen >> 1) & 1u);
-                        ++xseen;
+            for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
+                ++need;                           // this tile's gather
+                int xstep = 0;                    // step scanned up to while counting those epilogues
+                for (int s = 0; s < a.nsteps; ++s) {
+                    const TcStep& st = a.st[s];
+                    while (seen < need) {
+                        mbar_wait_relaxed(&a_bar, seen & 1u, kWalk && a.relaxed);
+                        ++seen;
                     }
-                }
-                tc_fence_after();
-                const uint32_t idesc = umma_idesc_bf16(kTcM, st.n);
-                const uint32_t a_addr = smem_u32(smem + st.a_off);
-                const uint32_t lbo_a = kTcM * 16, lbo_w = (uint32_t)st.n * 16;
-                const uint32_t d_addr = tmem_base + st.tmem_col;
-                for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
-                    const uint32_t stage = it % a.nstages;
-                    mbar_wait(&full_bar[stage], (it / a.nstages) & 1u);
+                    if (C > 1) {
+                        // every operand-writing epilogue before this step: (C - 1) peers each push 128 x n x 2 bytes
+                        for (; xstep < s; ++xstep) {
+                            if (a.st[xstep].epi != 1) continue;
+                            uint64_t* xb = &x_bar[xseen & 1u];
+                            mbar_arrive_expect_tx(xb, (C - 1u) * (uint32_t)a.st[xstep].n * (kTcM * 2u));
+                            mbar_wait(xb, (xseen >> 1) & 1u);
+                            ++xseen;
+                        }
+                    }
                     tc_fence_after();
-                    const uint32_t w_addr = smem_u32(smem + a.off_ring + stage * a.stage_bytes);
-                    const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
-                    for (int kk = 0; kk < ck / 16; ++kk) {
-                        const int q = k0 / 16 + kk;  // K16 step inside the A operand
-                        const uint64_t ad = umma_smem_desc(a_addr + (uint32_t)q * 2u * lbo_a, lbo_a, 128);
-                        const uint64_t bd = umma_smem_desc(w_addr + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
-                        umma_bf16(d_addr, ad, bd, idesc, st.acc || q > 0);
+                    const uint32_t idesc = umma_idesc_bf16(kTcM, st.n);
+                    const uint32_t a_addr = smem_u32(smem + st.a_off);
+                    const uint32_t lbo_a = kTcM * 16, lbo_w = (uint32_t)st.n * 16;
+                    const uint32_t d_addr = tmem_base + st.tmem_col;
+                    for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
+                        const uint32_t stage = it % a.nstages;
+                        mbar_wait(&full_bar[stage], (it / a.nstages) & 1u);
+                        tc_fence_after();
+                        const uint32_t w_addr = smem_u32(smem + a.off_ring + stage * a.stage_bytes);
+                        const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
+                        for (int kk = 0; kk < ck / 16; ++kk) {
+                            const int q = k0 / 16 + kk;  // K16 step inside the A operand
+                            const uint64_t ad = umma_smem_desc(a_addr + (uint32_t)q * 2u * lbo_a, lbo_a, 128);
+                            const uint64_t bd = umma_smem_desc(w_addr + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
+                            umma_bf16(d_addr, ad, bd, idesc, st.acc || q > 0);
+                        }
+                        umma_commit(&empty_bar[stage]);  // the stage is free once these MMAs have read it
                     }
-                    umma_commit(&empty_bar[stage]);  // the stage is free once these MMAs have read it
-                }
-                if (st.epi) {
-                    if (C > 1) umma_commit_multicast(&mma_bar, (uint16_t)((1u << C) - 1u));
-                    else umma_commit(&mma_bar);
-                    ++need;
+                    if (st.epi) {
+                        if (C > 1) umma_commit_multicast(&mma_bar, (uint16_t)((1u << C) - 1u));
+                        else umma_commit(&mma_bar);
+                        if (s != a.nsteps - 1) ++need;
+                    }
                 }
             }
         }
@@ -272,191 +324,256 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
             for (int c = tid; c < 2 * a.total_ch; c += kTcEpiThreads) ss[c] = src[c];
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous kernel's output (idx, feats, xyz) is complete
-        {
-            // Layer-0 operand, one thread per row: operand row k = feature channel k (k < D), then the three
-            // relative coordinates, then zero padding up to kp0.  Features are read with 16 independent 128-bit
-            // loads in flight per thread and stored as 16-byte (8 x bf16) core-matrix rows: thread m writes
-            // [(k / 8) * 128 + m], so a warp's stores are contiguous (no bank conflicts).
-            unsigned char* A0b = smem + a.st[0].a_off;
-            __nv_bfloat16* A0 = reinterpret_cast<__nv_bfloat16*>(A0b);
-            const int D = a.D, kp0 = a.kp0;
-            const int row = row0 + tid;
-            const bool valid = row < a.rows;
-            int j = 0, bs = 0;
-            if (valid) {
-                bs = row / a.K;
-                if (a.idx) {
-                    const int64_t jj = a.idx[row];
-                    j = jj < 0 ? 0 : (jj >= a.N ? a.N - 1 : (int)jj);
-                } else {
-                    j = row % a.K;  // group_all: row k of cloud b is point k
-                }
-            }
-            const int b = bs / a.S;
-            float rel[3] = {0.f, 0.f, 0.f};
-            if (valid) {
-                const float* p = a.xyz + ((size_t)b * a.N + j) * 3;
-                rel[0] = p[0]; rel[1] = p[1]; rel[2] = p[2];
-                if (a.new_xyz) {
-                    const float* c = a.new_xyz + (size_t)bs * 3;
-                    rel[0] = __fsub_rn(rel[0], c[0]); rel[1] = __fsub_rn(rel[1], c[1]); rel[2] = __fsub_rn(rel[2], c[2]);
-                }
-            }
-            const float* frow = D > 0 ? a.feats + ((size_t)b * a.N + j) * D : nullptr;
-            const bool vec = D > 0 && (D % 8) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
-            int kdone = 0;
-            if (vec) {
-                const int G = D / 8;
-                for (int g0 = 0; g0 < G; g0 += 8) {
-                    float4 v[16];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid && g0 + u < G) {
-                            v[2 * u] = __ldg(reinterpret_cast<const float4*>(frow + (g0 + u) * 8));
-                            v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(frow + (g0 + u) * 8 + 4));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (g0 + u < G) {
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[2 * u].x, v[2 * u].y);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2 * u].z, v[2 * u].w);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * u + 1].x, v[2 * u + 1].y);
-                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[2 * u + 1].z, v[2 * u + 1].w);
-                            *reinterpret_cast<uint4*>(A0b + ((size_t)(g0 + u) * kTcM + tid) * 16) =
-                                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                           *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-                        }
-                    }
-                }
-                kdone = D;
-            }
-            for (int k = kdone; k < kp0; ++k) {  // feature tail (unaligned D), relative coordinates, zero padding
-                float v = 0.f;
-                if (k < D) v = valid ? __ldg(frow + k) : 0.f;
-                else if (k - D < 3) v = (k - D) == 0 ? rel[0] : ((k - D) == 1 ? rel[1] : rel[2]);
-                A0[((size_t)(k >> 3) * kTcM + tid) * 8 + (k & 7)] = __float2bfloat16_rn(v);
-            }
-        }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        epi_bar_sync();       // the scale/shift tables are complete for every epilogue thread
-        mbar_arrive(&a_bar);  // event 0: the layer-0 operand is in place
-
         const uint32_t taddr_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
         const int m = tid;  // this thread's row = its TMEM lane
         uint32_t mma_phase = 0, xev = 0;
-        for (int s = 0; s < a.nsteps; ++s) {
-            const TcStep& st = a.st[s];
-            if (!st.epi) continue;
-            mbar_wait(&mma_bar, mma_phase & 1u);  // all C CTAs have finished the MMAs up to this step
-            ++mma_phase;
-            tc_fence_after();
-            const int slice0 = (int)rank * st.n;  // first channel of this CTA's N slice inside the step
-            const float* sc = ss + st.ss_idx + slice0;
-            const float* sh = ss + a.total_ch + st.ss_idx + slice0;
-            const uint32_t taddr = taddr_lane + st.tmem_col;
-            if (st.epi == 1) {
-                unsigned char* outp = smem + st.out_off + (size_t)(slice0 >> 3) * kTcM * 16;  // this slice's K groups
-                for (int c0 = 0; c0 < st.n; c0 += 32) {
-                    uint32_t r[2][16];
-                    tmem_ld16_issue(taddr + (uint32_t)c0, r[0]);
-                    const bool two = c0 + 16 < st.n;
-                    if (two) tmem_ld16_issue(taddr + (uint32_t)c0 + 16u, r[1]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && !two) break;
-                        const int cb = c0 + 16 * h;
-                        uint32_t packed[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            // two channels per step: one packed FFMA2 for scale/shift, one cvt.rn.relu.bf16x2 for ReLU +
-                            // rounding + packing (upper half = second channel)
-                            const float2 s2 = *reinterpret_cast<const float2*>(&sc[cb + 2 * i]);
-                            const float2 t2 = *reinterpret_cast<const float2*>(&sh[cb + 2 * i]);
-                            const float2 y = __ffma2_rn(make_float2(__uint_as_float(r[h][2 * i]), __uint_as_float(r[h][2 * i + 1])), s2, t2);
-                            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(packed[i]) : "f"(y.y), "f"(y.x));
-                        }
-                        // channels cb..cb+7 and cb+8..cb+15 are two K chunks of the next operand
-                        uint4* d0 = reinterpret_cast<uint4*>(outp + ((size_t)(cb >> 3) * kTcM + m) * 16);
-                        uint4* d1 = reinterpret_cast<uint4*>(outp + ((size_t)((cb >> 3) + 1) * kTcM + m) * 16);
-                        *d0 = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        *d1 = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                    }
-                }
-                fence_proxy_async();
-                if (C > 1) {
-                    // push the slice (contiguous: n / 8 K-groups x 128 rows x 16 B) into every peer's operand buffer
-                    epi_bar_sync();
-                    if (tid == 0) {
-                        const uint32_t src = smem_u32(outp), bytes = (uint32_t)st.n * (kTcM * 2u);
-                        const uint32_t bar = smem_u32(&x_bar[xev & 1u]);
-                        for (uint32_t q = 0; q < C; ++q)
-                            if (q != rank) bulk_copy_to_peer(mapa_shared(src, q), src, bytes, mapa_shared(bar, q));
-                    }
-                    ++xev;
-                }
-            } else {
-                // ---- max over each group's K rows ----
-                const int row = row0 + m;
+        for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
+            const int row0 = tile * kTcM;
+            // stamps: 0 tile start, 1 operand gathered, then per epilogue (accumulator ready, epilogue done); 15 = SM id
+            unsigned long long* stamp = (kWalk && a.probe && tid == 0 && rank == 0 && tile < a.probe_tiles) ? a.probe + (size_t)tile * 16 : nullptr;
+            int nstamp = 0;
+            if (stamp) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                stamp[15] = smid;
+                stamp[nstamp++] = clock64();
+            }
+            {
+                // Layer-0 operand, one thread per row: operand row k = feature channel k (k < D), then the three
+                // relative coordinates, then zero padding up to kp0.  Features are read with 16 independent 128-bit
+                // loads in flight per thread and stored as 16-byte (8 x bf16) core-matrix rows: thread m writes
+                // [(k / 8) * 128 + m], so a warp's stores are contiguous (no bank conflicts).
+                unsigned char* A0b = smem + a.st[0].a_off;
+                __nv_bfloat16* A0 = reinterpret_cast<__nv_bfloat16*>(A0b);
+                const int D = a.D, kp0 = a.kp0;
+                const int row = row0 + tid;
                 const bool valid = row < a.rows;
-                if (!a.pool_atomic) {
-                    // K in {32, 64, 128}: the warp's 32 rows belong to one group and every group lies in this tile
-                    float* pool = reinterpret_cast<float*>(smem + a.off_pool);  // [4 warps][n]
-                    for (int c0 = 0; c0 < st.n; c0 += 16) {
-                        uint32_t r[16];
-                        tmem_ld16_issue(taddr + (uint32_t)c0, r);
-                        tmem_ld_wait();
-                        unsigned int mine = 0;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float y = __fmaf_rn(__uint_as_float(r[i]), sc[c0 + i], sh[c0 + i]);
-                            y = (valid && y > 0.f) ? y : 0.f;  // post-ReLU values are >= +0: bits order like unsigned
-                            const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
-                            if (lane == i) mine = mx;
-                        }
-                        if (lane < 16) pool[warp * st.n + c0 + lane] = __uint_as_float(mine);
+                int j = 0, bs = 0;
+                if (valid) {
+                    bs = row / a.K;
+                    if (a.idx) {
+                        const int64_t jj = a.idx[row];
+                        j = jj < 0 ? 0 : (jj >= a.N ? a.N - 1 : (int)jj);
+                    } else {
+                        j = row % a.K;  // group_all: row k of cloud b is point k
                     }
-                    epi_bar_sync();
-                    const int wpg = a.K / 32;       // warps per group
-                    const int groups = kTcM / a.K;  // groups per tile
-                    const int g0 = row0 / a.K;      // first group (= b * S + s) of the tile
-                    for (int e = tid; e < groups * st.n; e += kTcEpiThreads) {
-                        const int g = e / st.n, c = e % st.n;
-                        if ((size_t)(g0 + g) * a.K >= (size_t)a.rows) continue;
-                        float v = pool[(g * wpg) * st.n + c];
-                        for (int w = 1; w < wpg; ++w) v = fmaxf(v, pool[(g * wpg + w) * st.n + c]);
-                        a.out[(size_t)(g0 + g) * a.cout + st.out_c0 + slice0 + c] = v;
+                }
+                const int b = bs / a.S;
+                float rel[3] = {0.f, 0.f, 0.f};
+                if (valid) {
+                    const float* p = a.xyz + ((size_t)b * a.N + j) * 3;
+                    rel[0] = p[0]; rel[1] = p[1]; rel[2] = p[2];
+                    if (a.new_xyz) {
+                        const float* c = a.new_xyz + (size_t)bs * 3;
+                        rel[0] = __fsub_rn(rel[0], c[0]); rel[1] = __fsub_rn(rel[1], c[1]); rel[2] = __fsub_rn(rel[2], c[2]);
                     }
-                    epi_bar_sync();  // pool is reused by the next pooled step
-                } else {
-                    const bool warp_uniform_group = (a.K % 32) == 0;
-                    const int wrow = row0 + warp * 32;
-                    const int g = (warp_uniform_group ? wrow : (valid ? row : 0)) / a.K;
-                    unsigned int* obase = reinterpret_cast<unsigned int*>(a.out) + (size_t)g * a.cout + st.out_c0 + slice0;
-                    for (int c0 = 0; c0 < st.n; c0 += 16) {
-                        uint32_t r[16];
-                        tmem_ld16_issue(taddr + (uint32_t)c0, r);
-                        tmem_ld_wait();
-                        unsigned int mine = 0;
+                }
+                const float* frow = D > 0 ? a.feats + ((size_t)b * a.N + j) * D : nullptr;
+                const bool vec = D > 0 && (D % 8) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
+                int kdone = 0;
+                if (vec) {
+                    const int G = D / 8;
+                    for (int g0 = 0; g0 < G; g0 += 8) {
+                        float4 v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float y = __fmaf_rn(__uint_as_float(r[i]), sc[c0 + i], sh[c0 + i]);
-                            y = (valid && y > 0.f) ? y : 0.f;
-                            if (warp_uniform_group) {
-                                const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
-                                if (lane == i) mine = mx;
-                            } else if (valid) {
-                                atomicMax(obase + c0 + i, __float_as_uint(y));
+                        for (int u = 0; u < 8; ++u) {
+                            v[2 * u] = v[2 * u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (valid && g0 + u < G) {
+                                v[2 * u] = __ldg(reinterpret_cast<const float4*>(frow + (g0 + u) * 8));
+                                v[2 * u + 1] = __ldg(reinterpret_cast<const float4*>(frow + (g0 + u) * 8 + 4));
                             }
                         }
-                        if (warp_uniform_group && lane < 16 && wrow < a.rows) atomicMax(obase + c0 + lane, mine);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (g0 + u < G) {
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[2 * u].x, v[2 * u].y);
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2 * u].z, v[2 * u].w);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * u + 1].x, v[2 * u + 1].y);
+                                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[2 * u + 1].z, v[2 * u + 1].w);
+                                *reinterpret_cast<uint4*>(A0b + ((size_t)(g0 + u) * kTcM + tid) * 16) =
+                                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+                            }
+                        }
                     }
+                    kdone = D;
+                }
+                for (int k = kdone; k < kp0; ++k) {  // feature tail (unaligned D), relative coordinates, zero padding
+                    float v = 0.f;
+                    if (k < D) v = valid ? __ldg(frow + k) : 0.f;
+                    else if (k - D < 3) v = (k - D) == 0 ? rel[0] : ((k - D) == 1 ? rel[1] : rel[2]);
+                    A0[((size_t)(k >> 3) * kTcM + tid) * 8 + (k & 7)] = __float2bfloat16_rn(v);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&a_bar);  // operand written / accumulator drained: later steps may proceed
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            if (tile == tile_first) epi_bar_sync();  // the scale/shift tables are complete for every epilogue thread
+            tc_fence_before();    // (later tiles) the previous tile's accumulator reads precede the MMAs this releases
+            mbar_arrive(&a_bar);  // the layer-0 operand is in place
+
+            for (int s = 0; s < a.nsteps; ++s) {
+                const TcStep& st = a.st[s];
+                if (!st.epi) continue;
+                mbar_wait(&mma_bar, mma_phase & 1u);  // all C CTAs have finished the MMAs up to this step
+                ++mma_phase;
+                tc_fence_after();
+                if (stamp && nstamp < 14) stamp[nstamp++] = clock64();
+                const int slice0 = (int)rank * st.n;  // first channel of this CTA's N slice inside the step
+                const float* sc = ss + st.ss_idx + slice0;
+                const float* sh = ss + a.total_ch + st.ss_idx + slice0;
+                const uint32_t taddr = taddr_lane + st.tmem_col;
+                if (st.epi == 1) {
+                    unsigned char* outp = smem + st.out_off + (size_t)(slice0 >> 3) * kTcM * 16;  // this slice's K groups
+                    // two 16-column loads in flight per wait (ptxas sinks a prefetch issued after the wait below the
+                    // arithmetic of the previous block, so the software-pipelined walk is kept for the pooled steps only)
+                    for (int c0 = 0; c0 < st.n; c0 += 32) {
+                        uint32_t r[2][16];
+                        tmem_ld16_issue(taddr + (uint32_t)c0, r[0]);
+                        const bool two = c0 + 16 < st.n;
+                        if (two) tmem_ld16_issue(taddr + (uint32_t)c0 + 16u, r[1]);
+                        tmem_ld_wait(r[0]);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (h == 1 && !two) break;
+                            const int cb = c0 + 16 * h;
+                            uint32_t packed[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                // two channels per step: one packed FFMA2 for scale/shift, one cvt.rn.relu.bf16x2 for ReLU +
+                                // rounding + packing (upper half = second channel)
+                                const float2 s2 = *reinterpret_cast<const float2*>(&sc[cb + 2 * i]);
+                                const float2 t2 = *reinterpret_cast<const float2*>(&sh[cb + 2 * i]);
+                                const float2 y = __ffma2_rn(make_float2(__uint_as_float(r[h][2 * i]), __uint_as_float(r[h][2 * i + 1])), s2, t2);
+                                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(packed[i]) : "f"(y.y), "f"(y.x));
+                            }
+                            // channels cb..cb+7 and cb+8..cb+15 are two K chunks of the next operand
+                            uint4* d0 = reinterpret_cast<uint4*>(outp + ((size_t)(cb >> 3) * kTcM + m) * 16);
+                            uint4* d1 = reinterpret_cast<uint4*>(outp + ((size_t)((cb >> 3) + 1) * kTcM + m) * 16);
+                            *d0 = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            *d1 = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                        }
+                    }
+                    fence_proxy_async();
+                    if (C > 1) {
+                        // push the slice (contiguous: n / 8 K-groups x 128 rows x 16 B) into every peer's operand buffer
+                        epi_bar_sync();
+                        if (tid == 0) {
+                            const uint32_t src = smem_u32(outp), bytes = (uint32_t)st.n * (kTcM * 2u);
+                            const uint32_t bar = smem_u32(&x_bar[xev & 1u]);
+                            for (uint32_t q = 0; q < C; ++q)
+                                if (q != rank) bulk_copy_to_peer(mapa_shared(src, q), src, bytes, mapa_shared(bar, q));
+                        }
+                        ++xev;
+                    }
+                } else {
+                    // ---- max over each group's K rows ----
+                    const int row = row0 + m;
+                    const bool valid = row < a.rows;
+                    if (!a.pool_atomic) {
+                        // K in {32, 64, 128}: the warp's 32 rows belong to one group and every group lies in this tile
+                        float* pool = reinterpret_cast<float*>(smem + a.off_pool);  // [4 warps][n]
+                        // relu(max over rows) == max over rows of relu: the warp reduces the RAW scale/shift results as
+                        // SIGNED integers (any non-negative float beats every negative one and non-negative floats order
+                        // like their bits; an all-negative column yields some negative value) and the ReLU is applied
+                        // once, where the pooled value is read below.  Four columns per step: two LDS.128 for scale and
+                        // shift, two FFMA2, four warp reductions, one 16-byte store of the (uniform) results.
+                        if constexpr (!kWalk) {
+                            // three CTAs per SM, 96 registers: 16 independent reductions per accumulator block, each
+                            // lane keeping one of them
+                            for (int c0 = 0; c0 < st.n; c0 += 16) {
+                                uint32_t r[16];
+                                tmem_ld16_issue(taddr + (uint32_t)c0, r);
+                                tmem_ld_wait(r);
+                                unsigned int mine = 0;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    float y = __fmaf_rn(__uint_as_float(r[i]), sc[c0 + i], sh[c0 + i]);
+                                    y = (valid && y > 0.f) ? y : 0.f;  // post-ReLU values are >= +0: bits order like unsigned
+                                    const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
+                                    if (lane == i) mine = mx;
+                                }
+                                if (lane < 16) pool[warp * st.n + c0 + lane] = __uint_as_float(mine);
+                            }
+                        } else {
+                            // relu(max over rows) == max over rows of relu: the warp reduces the RAW scale/shift results
+                            // as SIGNED integers (any non-negative float beats every negative one and non-negative floats
+                            // order like their bits; an all-negative column yields some negative value) and the ReLU is
+                            // applied once, where the pooled value is read below.  Per 16 columns: LDS.128 for scale and
+                            // shift, 8 FFMA2, 16 independent warp reductions, then four 16-byte stores of the (uniform)
+                            // results; the next 16 columns are already loading from TMEM.
+                            float* prow = pool + warp * st.n;
+                            auto pooled = [&](auto masked) {
+                                tmem_for_each16(taddr, st.n, [&](const uint32_t (&r)[16], int c0) {
+                                    int mx[16];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float4 s4 = *reinterpret_cast<const float4*>(&sc[c0 + 4 * q]);
+                                        const float4 t4 = *reinterpret_cast<const float4*>(&sh[c0 + 4 * q]);
+                                        const float2 y01 =
+                                            __ffma2_rn(make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])),
+                                                       make_float2(s4.x, s4.y), make_float2(t4.x, t4.y));
+                                        const float2 y23 =
+                                            __ffma2_rn(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])),
+                                                       make_float2(s4.z, s4.w), make_float2(t4.z, t4.w));
+                                        int v[4] = {__float_as_int(y01.x), __float_as_int(y01.y), __float_as_int(y23.x),
+                                                    __float_as_int(y23.y)};
+                                        if (decltype(masked)::value) {  // rows past the end (last tile only): below every value
+#pragma unroll
+                                            for (int i = 0; i < 4; ++i) v[i] = valid ? v[i] : (int)0x80000000;
+                                        }
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) mx[4 * q + i] = __reduce_max_sync(0xffffffffu, v[i]);
+                                    }
+                                    if (lane == 0) {
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            *reinterpret_cast<int4*>(prow + c0 + 4 * q) =
+                                                make_int4(mx[4 * q], mx[4 * q + 1], mx[4 * q + 2], mx[4 * q + 3]);
+                                    }
+                                });
+                            };
+                            if (row0 + kTcM <= a.rows) pooled(std::false_type{});
+                            else pooled(std::true_type{});
+                        }
+                        epi_bar_sync();
+                        const int wpg = a.K / 32;       // warps per group
+                        const int groups = kTcM / a.K;  // groups per tile
+                        const int g0 = row0 / a.K;      // first group (= b * S + s) of the tile
+                        for (int e = tid; e < groups * st.n; e += kTcEpiThreads) {
+                            const int g = e / st.n, c = e % st.n;
+                            if ((size_t)(g0 + g) * a.K >= (size_t)a.rows) continue;
+                            float v = pool[(g * wpg) * st.n + c];
+                            for (int w = 1; w < wpg; ++w) v = fmaxf(v, pool[(g * wpg + w) * st.n + c]);
+                            a.out[(size_t)(g0 + g) * a.cout + st.out_c0 + slice0 + c] = v > 0.f ? v : 0.f;  // the ReLU
+                        }
+                        epi_bar_sync();  // pool is reused by the next pooled step
+                    } else {
+                        const bool warp_uniform_group = (a.K % 32) == 0;
+                        const int wrow = row0 + warp * 32;
+                        const int g = (warp_uniform_group ? wrow : (valid ? row : 0)) / a.K;
+                        unsigned int* obase = reinterpret_cast<unsigned int*>(a.out) + (size_t)g * a.cout + st.out_c0 + slice0;
+                        tmem_for_each16(taddr, st.n, [&](const uint32_t (&r)[16], int c0) {
+                            unsigned int mine = 0;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                float y = __fmaf_rn(__uint_as_float(r[i]), sc[c0 + i], sh[c0 + i]);
+                                y = (valid && y > 0.f) ? y : 0.f;
+                                if (warp_uniform_group) {
+                                    const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
+                                    if (lane == i) mine = mx;
+                                } else if (valid) {
+                                    atomicMax(obase + c0 + i, __float_as_uint(y));
+                                }
+                            }
+                            if (warp_uniform_group && lane < 16 && wrow < a.rows) atomicMax(obase + c0 + lane, mine);
+                        });
+                    }
+                }
+                if (stamp && nstamp < 14) stamp[nstamp++] = clock64();
+                if (s != a.nsteps - 1) {  // the last (pooled) step: the next tile's gather event stands for it
+                    tc_fence_before();
+                    mbar_arrive(&a_bar);  // operand written / accumulator drained: later steps may proceed
+                }
+            }
         }
     }
 
@@ -549,8 +666,18 @@ static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false) {
     const uint32_t limit = 225 * 1024;
     auto nchunks = [&](int kp, int nc) { const int ck = chunk_rows(kp, nc); return (kp + ck - 1) / ck; };
     int total_chunks = nchunks(p.kp0, n0c) + h2 * h1 * (nchunks(n0, n1c) + nchunks(n1h, n2c));
-    p.nstages = dense ? 2 : kTcMaxStages;
+    p.nstages = kTcMaxStages;
     while (p.nstages > 2 && (fixed + p.nstages * p.stage_bytes > limit || (int)p.nstages > total_chunks)) --p.nstages;
+    if (dense) {
+        // the deepest ring that does not cost a co-resident CTA (3 is the register-file bound of the kernel)
+        auto ctas = [&](uint32_t ns) {
+            const uint32_t per_sm = 228u * 1024u / (fixed + ns * p.stage_bytes + 1024u);
+            return per_sm < 3u ? per_sm : 3u;
+        };
+        p.nstages = (uint32_t)tuning("sa_mlp.ring", kTcMaxStages);
+        if (p.nstages < 2 || p.nstages > (uint32_t)kTcMaxStages) p.nstages = kTcMaxStages;
+        while (p.nstages > 2 && ctas(p.nstages) < ctas(2)) --p.nstages;
+    }
     if (fixed + p.nstages * p.stage_bytes > limit) return p;
     p.off_ring = 0;
     const uint32_t off_x = p.nstages * p.stage_bytes;
@@ -625,6 +752,13 @@ int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, int C, void* blob, cudaStream_
     return PCST_OK;
 }
 
+static unsigned long long* g_tc_probe = nullptr;
+static int g_tc_probe_tiles = 0;
+void sa_mlp_tc_set_probe(unsigned long long* buf, int tiles) {
+    g_tc_probe = buf;
+    g_tc_probe_tiles = buf ? tiles : 0;
+}
+
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
                   int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream) {
     const size_t rows_sz = (size_t)B * S * K;
@@ -651,10 +785,36 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     a.pool_atomic = !(K == 32 || K == 64 || K == 128);
     a.cluster = (uint32_t)C;
     if (a.pool_atomic) PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * cout[2] * sizeof(float), stream));
-    PCST_CUDA(cudaFuncSetAttribute(sa_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     const int tiles = (a.rows + kTcM - 1) / kTcM;
+    // three CTAs per SM pay off when tiles queue up on every SM and the stage's shared memory allows a third one
+    const int regs = tuning("sa_mlp.regs", 0);  // 0 = auto, else 96 / 168 (A/B measurements)
+    const bool three = regs ? regs == 96 : (tiles > 2 * kNumSMs && (p.smem_bytes + 1024u) * 3u <= 228u * 1024u);
+    auto kernel = three ? sa_mlp_tc_kernel<96, false> : sa_mlp_tc_kernel<168, true>;
+    a.probe = g_tc_probe; a.probe_tiles = g_tc_probe_tiles;
+    a.relaxed = tiles > kNumSMs && tuning("sa_mlp.backoff", 1) == 1;
+    PCST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    if (tuning("sa_mlp.carveout", 0) == 1)
+        PCST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    a.ntiles = tiles;
+    // More tiles than the machine holds at once (C == 1 by construction): as many CTAs as are co-resident, each walking
+    // tiles with stride gridDim -- barriers, TMEM and the scale/shift tables are set up once and the weight ring keeps
+    // streaming across tile boundaries.  TMEM columns bound the co-residency too (the occupancy API does not know).
+    unsigned grid = (unsigned)tiles * C;
+    if (C == 1 && !three && tiles > kNumSMs && tuning("sa_mlp.persistent", 1) == 1) {
+        // co-resident CTAs per SM from the kernel's own footprint: shared memory (228 KiB per SM at the maximum
+        // carve-out, 1 KiB reserved per CTA), registers (64 Ki per SM, allocated per warp in units of 256) and TMEM
+        // columns (512 per SM, which the occupancy API does not model)
+        cudaFuncAttributes fa;
+        PCST_CUDA(cudaFuncGetAttributes(&fa, kernel));
+        const int regs_per_cta = (kTcThreads / 32) * ((fa.numRegs * 32 + 255) / 256 * 256);
+        int occ = (int)(228u * 1024u / (p.smem_bytes + (uint32_t)fa.sharedSizeBytes + 1024u));
+        if (occ > 65536 / regs_per_cta) occ = 65536 / regs_per_cta;
+        if (occ > 512 / (int)p.tmem_cols) occ = 512 / (int)p.tmem_cols;
+        if (occ < 1) occ = 1;
+        if ((unsigned)(occ * kNumSMs) < grid) grid = (unsigned)(occ * kNumSMs);
+    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)tiles * C);
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = p.smem_bytes;
     cfg.stream = stream;
@@ -667,7 +827,7 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = tuning("sa_mlp.pdl", 1) == 1 ? 2 : 1;  // 2 = off (A/B measurements)
-    PCST_CUDA(cudaLaunchKernelEx(&cfg, sa_mlp_tc_kernel, a));
+    PCST_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
     return PCST_OK;
 }
 

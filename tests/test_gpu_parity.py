@@ -326,6 +326,45 @@ def test_sa_mlp_tensor_core_every_cluster_split(api, dev, oracle, cluster, mlp, 
     np.testing.assert_allclose(outs[cluster].cpu().numpy(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("mlp,D,K,clouds", [([64, 64, 128], 0, 32, 2400), ([128, 128, 256], 128, 64, 1400), ([64, 96, 128], 5, 24, 3000)])
+def test_sa_mlp_tensor_core_persistent_tile_walk(api, dev, oracle, mlp, D, K, clouds):
+    """More row tiles than the machine holds at once: each CTA walks several tiles (barrier phases, the weight
+    ring and the accumulator columns carried from tile to tile).  Bit-identical to one CTA per tile, and within the
+    bf16 tolerance of the oracle on a sample of the groups.  Third case: the atomic pooling path (K % 32 != 0)."""
+    from pointcloud_style_transfer_b200 import _lib
+    torch.manual_seed(11)
+    sa = api.enc.SetAbstraction(None, None, None, in_channel=D, mlp=mlp, group_all=True).eval().to(dev)
+    sa.mlp_precision = 1
+    g = torch.Generator().manual_seed(5)
+    for bn in sa.mlp_bns:
+        bn.running_mean.copy_(torch.randn(bn.num_features, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(bn.num_features, generator=g) * 0.5 + 0.75)
+    xyz = S.uniform_cloud(43, clouds, K)
+    feats = torch.randn(clouds, K, D, generator=torch.Generator().manual_seed(6)) if D else None
+    ws, scs, shs = sa._folded()
+    couts = [int(w.shape[0]) for w in ws]
+    packed = api.ops.sa_mlp_pack(ws, scs, shs, D, 1, 1)
+    fd = None if feats is None else feats.to(dev)
+    outs = {}
+    try:
+        # (walk, register variant): the walking kernel, the same kernel with one CTA per tile, and the automatic choice
+        # (narrow stages take the three-CTAs-per-SM variant, which never walks)
+        for mode in ((1, 168), (2, 168), (0, 0)):
+            _lib.set_tuning("sa_mlp.persistent", mode[0])
+            _lib.set_tuning("sa_mlp.regs", mode[1])
+            outs[mode] = api.ops.sa_mlp_max(xyz.to(dev), fd, None, None, packed, couts, 1, 1)[:, 0, :mlp[2]]
+    finally:
+        _lib.set_tuning("sa_mlp.persistent", 0)
+        _lib.set_tuning("sa_mlp.regs", 0)
+    assert torch.equal(outs[(1, 168)], outs[(2, 168)])
+    assert torch.equal(outs[(1, 168)], outs[(0, 0)])
+    sd = {k: v.detach().cpu().numpy() for k, v in sa.state_dict().items()}
+    pick = np.r_[0:8, clouds // 2:clouds // 2 + 8, clouds - 8:clouds]  # first / middle / last tiles
+    pts = (xyz if feats is None else torch.cat([xyz, feats], -1))[pick][:, None]
+    ref = oracle.apply_mlp(pts.numpy(), oracle.layers_from_state_dict(sd, ""))[:, :, 0]
+    np.testing.assert_allclose(outs[(1, 168)][pick].cpu().numpy(), ref, rtol=2e-2, atol=2e-2)
+
+
 def test_sa_mlp_tensor_core_ragged_groups(api, dev, oracle):
     """K not a multiple of 32 and a partial last row tile exercise the per-element pooling path."""
     torch.manual_seed(0)

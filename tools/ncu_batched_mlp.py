@@ -11,18 +11,27 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pointcloud_style_transfer_b200 import ops, synthetic as S  # noqa: E402
 from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder  # noqa: E402
 
+from pointcloud_style_transfer_b200 import _lib  # noqa: E402
+
+for kv in filter(None, os.environ.get("TUNE", "").split(",")):  # e.g. TUNE=sa_mlp.persistent=2,sa_mlp.regs=168
+    k, v = kv.split("=")
+    _lib.set_tuning(k, int(v))
 dev = torch.device("cuda:0")
 B, N = 32, 16384
 x = torch.cat([S.lidar_scan(i, N) for i in range(B)], 0).to(dev)
 torch.manual_seed(42)
 enc = PointNet2Encoder(feature_dim=256, mlp_precision=1).eval().to(dev)
 with torch.no_grad():
-    for rep in range(3):
+    logs = []
+    for rep in range(int(os.environ.get("REPS", "3"))):
         ops.start_event_log()
         torch.manual_seed(1)
         enc(x)
-        log = ops.stop_event_log()
-print("per-op us (last pass):", {k: [round(v * 1e3, 1) for v in vs] for k, vs in log.items()})
+        logs.append(ops.stop_event_log())
+# median over the passes after the first (one pass under ncu: REPS=1)
+keep = logs[1:] or logs
+log = {k: [sorted(l[k][i] for l in keep)[len(keep) // 2] for i in range(len(v))] for k, v in logs[-1].items()}
+print("per-op us (median pass):", {k: [round(v * 1e3, 1) for v in vs] for k, vs in log.items()})
 rows = [B * 512 * 32, B * 128 * 64, B * 128]
 macs = [3 * 64 + 64 * 64 + 64 * 128, 131 * 128 + 128 * 128 + 128 * 256, 259 * 256 + 256 * 512 + 512 * 256]
 for name, r, m, t in zip(("SA1", "SA2", "SA3"), rows, macs, log["pcst_sa_mlp_max_f32"]):
