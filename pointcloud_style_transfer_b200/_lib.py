@@ -97,6 +97,12 @@ def load() -> ctypes.CDLL:
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # PCST_TUNE="key=value,key=value": tuning knobs for a whole process (A/B measurements without code changes)
+    for kv in filter(None, os.environ.get("PCST_TUNE", "").split(",")):
+        key, _, value = kv.partition("=")
+        status = lib.pcst_set_tuning(key.strip().encode(), int(value))
+        if status != PCST_OK:
+            raise PcstError(status, lib.pcst_last_error().decode("utf-8", "replace"))
     return lib
 
 

@@ -37,8 +37,6 @@ static std::map<std::string, int>& tune_map() {
         {"sa_mlp.pdl", 0},            // 0/1 = programmatic dependent launch of the tcgen05 MLP kernel on, 2 = off
         {"sa_mlp.regs", 0},           // 0 = auto, 96 / 168 = register budget variant of the tcgen05 MLP kernel
         {"sa_mlp.backoff", 0},        // 0/1 = producer / MMA threads pause between barrier polls at throughput shapes, 2 = off
-        {"sa_mlp.carveout", 0},       // 1 = ask for the maximum shared-memory carve-out (A/B measurements)
-        {"sa_mlp.ring", 0},           // 0 = auto, 2..4 = weight ring stages at throughput shapes (A/B measurements)
         {"sa_mlp.persistent", 0},     // 0/1 = CTAs walk several row tiles when tiles exceed the machine, 2 = one CTA per tile
     };
     return m;

@@ -674,8 +674,7 @@ static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false) {
             const uint32_t per_sm = 228u * 1024u / (fixed + ns * p.stage_bytes + 1024u);
             return per_sm < 3u ? per_sm : 3u;
         };
-        p.nstages = (uint32_t)tuning("sa_mlp.ring", kTcMaxStages);
-        if (p.nstages < 2 || p.nstages > (uint32_t)kTcMaxStages) p.nstages = kTcMaxStages;
+        p.nstages = kTcMaxStages;
         while (p.nstages > 2 && ctas(p.nstages) < ctas(2)) --p.nstages;
     }
     if (fixed + p.nstages * p.stage_bytes > limit) return p;
@@ -793,8 +792,6 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     a.probe = g_tc_probe; a.probe_tiles = g_tc_probe_tiles;
     a.relaxed = tiles > kNumSMs && tuning("sa_mlp.backoff", 1) == 1;
     PCST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    if (tuning("sa_mlp.carveout", 0) == 1)
-        PCST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = tiles;
     // More tiles than the machine holds at once (C == 1 by construction): as many CTAs as are co-resident, each walking
     // tiles with stride gridDim -- barriers, TMEM and the scale/shift tables are set up once and the weight ring keeps

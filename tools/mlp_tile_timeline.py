@@ -1,7 +1,7 @@
 """Per-tile timeline of the tcgen05 shared-MLP kernel at the throughput shape (32 scans x 16 384 points), from the SM-clock
 stamps pcst_sa_mlp_set_probe records: mean cycles per phase (gather, wait for the accumulator, epilogue, ...) per stage.
 
-    [TUNE=key=value,...] python tools/mlp_tile_timeline.py
+    [PCST_TUNE=key=value,...] python tools/mlp_tile_timeline.py
 """
 import os
 import sys
@@ -13,9 +13,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pointcloud_style_transfer_b200 import _lib, ops, synthetic as S  # noqa: E402
 from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder  # noqa: E402
 
-for kv in filter(None, os.environ.get("TUNE", "").split(",")):
-    k, v = kv.split("=")
-    _lib.set_tuning(k, int(v))
 dev = torch.device("cuda:0")
 B, N = int(os.environ.get("SCANS", "32")), 16384
 x = torch.cat([S.lidar_scan(i, N) for i in range(B)], 0).to(dev)

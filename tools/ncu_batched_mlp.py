@@ -11,11 +11,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pointcloud_style_transfer_b200 import ops, synthetic as S  # noqa: E402
 from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder  # noqa: E402
 
-from pointcloud_style_transfer_b200 import _lib  # noqa: E402
-
-for kv in filter(None, os.environ.get("TUNE", "").split(",")):  # e.g. TUNE=sa_mlp.persistent=2,sa_mlp.regs=168
-    k, v = kv.split("=")
-    _lib.set_tuning(k, int(v))
 dev = torch.device("cuda:0")
 B, N = 32, 16384
 x = torch.cat([S.lidar_scan(i, N) for i in range(B)], 0).to(dev)
