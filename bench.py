@@ -224,6 +224,7 @@ def main():
     def timed(fn, steps):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
+        fn()                                           # untimed: a rank that waited at the barrier has an idle GPU
         for a, b in evs:
             flush.fill_(1)                             # L2 flush between timed iterations (untimed)
             a.record()
@@ -335,6 +336,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allgather(v):
+        if world == 1:
+            return [v]
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        out = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return [float(x) for x in out.tolist()]
+
+    rank_ms = allgather(sum(ms_dev) / K)     # per-rank view of the same timed steps (diagnosis of a slow rank)
+    rank_worst = allgather(max(ms_dev))
     t_dev = allmax(sum(ms_dev)) / K          # ms per step, max over ranks
     t_e2e = allmax(sum(ms_e2e)) / K
     t_ch = allmax(ch_ms)
@@ -360,6 +371,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "points": N_POINTS, "feature_dim": FEATURE_DIM,
                        "scans_per_gpu": 1, "l2": "flushed between timed iterations (256 MiB write)",
+                       "timing": "CUDA events around each of the K steps, summed; one untimed step after the opening barrier",
                        "launch": "one CUDA-graph replay per step (stage-2 sampling on a parallel graph branch)",
                        "mlp_precision": args.mlp_precision},
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": t_e2e,
@@ -383,6 +395,7 @@ def main():
                                      "peak_source": "measured in this run" if fp32_measured else "computed",
                                      "frac_if_both_directions_counted": 2 * ch_tflops / fp32_peak}},
             "clocks": clocks,
+            "ranks": {"ms_per_step": rank_ms, "slowest_single_step_ms": rank_worst},
         }
         if t_b is not None:
             line["batched"] = {"metric": "SA points/sec, %d x 120k-pt scans per GPU in one graph (= concurrent 16-CTA FPS clusters)" % args.batched_scans,
