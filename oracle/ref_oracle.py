@@ -18,7 +18,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import numpy as np
 

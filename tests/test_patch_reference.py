@@ -1,7 +1,6 @@
 """CPU, build container only: ``patch_reference()`` swaps the hot-path symbols inside an importable checkout of the
 reference and the drop-in modules keep the reference's parameter names (so its checkpoints load).  Skipped where the
 reference is not mounted (the GPU box)."""
-import importlib
 import os
 import subprocess
 import sys

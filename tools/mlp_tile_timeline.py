@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pointcloud_style_transfer_b200 import _lib, ops, synthetic as S  # noqa: E402
+from pointcloud_style_transfer_b200 import _lib, synthetic as S  # noqa: E402
 from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder  # noqa: E402
 
 dev = torch.device("cuda:0")
