@@ -214,7 +214,8 @@ def main():
     genc = GraphedEncoder(enc)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    sampler = ClockSampler(local_rank)
+    # every rank samples its own GPU; with several ranks on one host poll less often (NVML calls share driver locks)
+    sampler = ClockSampler(local_rank, period=0.002 if world == 1 else 0.01)
     sampler.start()
     torch.manual_seed(1234 + rank)
     for _ in range(W):
@@ -346,6 +347,8 @@ def main():
 
     rank_ms = allgather(sum(ms_dev) / K)     # per-rank view of the same timed steps (diagnosis of a slow rank)
     rank_worst = allgather(max(ms_dev))
+    rank_mhz = allgather(float(clocks["sm_mhz"]) if clocks["sm_mhz"] is not None else -1.0)
+    rank_throttled = allgather(float(len([r for r in clocks["reasons"] if not r.startswith("nvml_unavailable")])))
     t_dev = allmax(sum(ms_dev)) / K          # ms per step, max over ranks
     t_e2e = allmax(sum(ms_e2e)) / K
     t_ch = allmax(ch_ms)
@@ -395,7 +398,8 @@ def main():
                                      "peak_source": "measured in this run" if fp32_measured else "computed",
                                      "frac_if_both_directions_counted": 2 * ch_tflops / fp32_peak}},
             "clocks": clocks,
-            "ranks": {"ms_per_step": rank_ms, "slowest_single_step_ms": rank_worst},
+            "ranks": {"ms_per_step": rank_ms, "slowest_single_step_ms": rank_worst, "sm_mhz": rank_mhz,
+                      "throttle_reasons_seen": rank_throttled},
         }
         if t_b is not None:
             line["batched"] = {"metric": "SA points/sec, %d x 120k-pt scans per GPU in one graph (= concurrent 16-CTA FPS clusters)" % args.batched_scans,
