@@ -31,6 +31,12 @@ def _oracle_pair(a, b, form):
     return torch.from_numpy(rows), torch.from_numpy(cols)
 
 
+def _oracle_knn(q, r, k):
+    from oracle import ref_oracle as O
+    d, i = O.knn(q.numpy(), r.numpy(), k)
+    return torch.from_numpy(d), torch.from_numpy(i)
+
+
 class _ToyEncoder(torch.nn.Module):
     def forward(self, x):  # [S,N,3] -> [S,4]: any per-scan function will do for the plumbing test
         return torch.cat([x.mean(dim=1), x.abs().amax(dim=(1, 2))[:, None]], dim=1)
@@ -59,7 +65,10 @@ def _worker(rank, world, port, q):
         ok_gather = ok_gather and torch.equal(D.all_gather_ragged(even[:, elo:ehi].contiguous(), total=64), even)
         scans = S.uniform_cloud(5, 5, 64)
         feats = D.encode_scans_sharded(_ToyEncoder(), scans)
-        q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy(), cd1.numpy(), cdm1.numpy(), cde.numpy()))
+        # 3-NN with the queries sharded and the (ragged) reference shards all-gathered: results stay sharded
+        kd, ki = D.knn_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), 3, knn_fn=_oracle_knn)
+        q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy(), cd1.numpy(), cdm1.numpy(), cde.numpy(),
+               (lo, hi), kd.numpy(), ki.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -81,7 +90,10 @@ def test_query_sharded_chamfer_and_scan_sharding_world2(oracle):
     scans = S.uniform_cloud(5, 5, 64)
     ref_feats = _ToyEncoder()(scans).numpy()
     ref_e = oracle.chamfer_distance_chunked_optimized(pred.numpy()[:, :5], target.numpy())
-    for rank, ok_gather, cd, cdm, feats, cd1, cdm1, cde in res:
+    ref_kd, ref_ki = oracle.knn(pred.numpy(), target.numpy(), 3)
+    for rank, ok_gather, cd, cdm, feats, cd1, cdm1, cde, (lo, hi), kd, ki in res:
+        np.testing.assert_array_equal(ki, ref_ki[:, lo:hi])   # indices refer to the gathered (rank-ordered) references
+        np.testing.assert_array_equal(kd, ref_kd[:, lo:hi])
         assert ok_gather
         np.testing.assert_allclose(cd, ref, rtol=1e-6)
         np.testing.assert_allclose(cdm, refm, rtol=1e-6)
