@@ -72,6 +72,23 @@ def test_tuning_knobs(lib):
         _lib.set_tuning("no.such.knob", 1)
 
 
+def test_pcst_tune_environment_is_applied_at_load():
+    """PCST_TUNE="key=value,..." sets knobs for a whole process when the library is loaded; an unknown key fails loudly."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("from pointcloud_style_transfer_b200 import _lib; _lib.load(); "
+            "print(_lib.get_tuning('fps.cluster'), _lib.get_tuning('sa_mlp.regs'))")
+    env = dict(os.environ, PCST_TUNE="fps.cluster=8, sa_mlp.regs=168", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["8", "168"]
+    env["PCST_TUNE"] = "no.such.knob=1"
+    bad = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
+    assert bad.returncode != 0 and "unknown key" in bad.stderr
+
+
 def test_cpu_tensors_raise_loudly():
     import torch
 
