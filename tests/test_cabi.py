@@ -64,6 +64,30 @@ def test_workspace_queries(lib):
     assert lib.pcst_nn_min_workspace_bytes(0, 1, 1) == 0
 
 
+def test_shared_mlp_plan_queries_are_host_only(lib):
+    """The launch plan of the shared MLP (cluster split, packed-blob size) is plain host arithmetic: no GPU needed.
+    Shapes: the three stages of the reference encoder (models/pointnet2_encoder.py:117-119) on 1 and 32 scans."""
+    import ctypes
+    C3 = ctypes.c_int * 3
+    sa1, sa2, sa3 = (512, 32, 0, (64, 64, 128)), (128, 64, 128, (128, 128, 256)), (1, 128, 256, (256, 512, 256))
+    for S_, K, D, c in (sa1, sa2, sa3):
+        assert lib.pcst_sa_mlp_pick_cluster(1, S_, K, D, C3(*c), 0) == 1           # fp32 path never splits
+        assert lib.pcst_sa_mlp_pick_cluster(32, S_, K, D, C3(*c), 1) in (1, 2, 4)  # many tiles: little or no split
+    # one scan: SA1 has 128 row tiles (no room to split), SA2 64 (two CTAs per tile), SA3 one (eight)
+    assert [lib.pcst_sa_mlp_pick_cluster(1, S_, K, D, C3(*c), 1) for S_, K, D, c in (sa1, sa2, sa3)] == [1, 2, 8]
+    for S_, K, D, c in (sa1, sa2, sa3):
+        kp0 = -(-(3 + D) // 16) * 16
+        weights = 2 * (kp0 * c[0] + c[0] * c[1] + c[1] * c[2])  # bf16, layer-0 K padded to 16
+        for cl in (1, 2, 4):
+            n = lib.pcst_sa_mlp_packed_bytes(D, C3(*c), 1, cl)
+            assert n >= weights + 2 * 4 * sum(c) and n < 1.1 * weights + 8 * sum(c) + 4096
+        assert lib.pcst_sa_mlp_packed_bytes(D, C3(*c), 0, 1) >= 4 * ((3 + D) * c[0] + c[0] * c[1] + c[1] * c[2])
+    assert lib.pcst_sa_mlp_packed_bytes(0, C3(64, 64, 128), 1, 8) == 0              # 64 / 8 columns per CTA: no such plan
+    assert lib.pcst_sa_mlp_packed_bytes(0, C3(64, 64, 100), 1, 1) == 0              # widths must be multiples of 32
+    # wider than the tensor-core path takes (Cout_2 > 512): the fp32 layout is what both precisions pack
+    assert lib.pcst_sa_mlp_packed_bytes(0, C3(64, 64, 1024), 1, 1) == lib.pcst_sa_mlp_packed_bytes(0, C3(64, 64, 1024), 0, 1)
+
+
 def test_tuning_knobs(lib):
     _lib.set_tuning("nn_min.splits", 3)
     assert _lib.get_tuning("nn_min.splits") == 3
