@@ -35,7 +35,7 @@ static std::map<std::string, int>& tune_map() {
         {"fps.prune", 0},             // 0/1 = bounding-box skip test on, 2 = off
         {"sa_mlp.variant", 0},
         {"sa_mlp.pdl", 0},            // 0/1 = programmatic dependent launch of the tcgen05 MLP kernel on, 2 = off
-        {"sa_mlp.regs", 0},           // 0 = auto, 96 / 168 = register budget variant of the tcgen05 MLP kernel
+        {"sa_mlp.regs", 0},           // 0 = auto, 80 / 168 = register budget variant of the tcgen05 MLP kernel
         {"sa_mlp.backoff", 0},        // 0/1 = producer / MMA threads pause between barrier polls at throughput shapes, 2 = off
         {"sa_mlp.persistent", 0},     // 0/1 = CTAs walk several row tiles when tiles exceed the machine, 2 = one CTA per tile
     };

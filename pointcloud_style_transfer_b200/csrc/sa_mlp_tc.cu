@@ -195,10 +195,13 @@ __global__ void tc_pack_ss_kernel(const float* __restrict__ scale, const float* 
 
 // Two instantiations.  <168, true>: CTAs walk several row tiles when there are more tiles than the machine holds (two
 // CTAs per SM; barriers, TMEM and the scale/shift tables set up once, the weight ring streaming across tile boundaries).
-// <96, false>: one tile per CTA within the register budget that lets THREE CTAs share an SM.  A CTA's six warps land
-// 2/2/1/1 on the four SM partitions (16 Ki registers each), so three CTAs put five warps on a partition: 5 x 32 x 96
-// registers fit, 5 x 32 x 112 do not.  The narrow stages (SA1: 3 -> 64 -> 64 -> 128) are bound by the latency of a
-// tile's serial chain, so the third resident tile is worth more than the walk.
+// <80, false>: one tile per CTA within the register budget that lets FOUR CTAs share an SM.  A CTA's six warps land
+// 2/2/1/1 on the four SM partitions (16 Ki registers each), so four CTAs put six warps on a partition: 6 x 32 x 80
+// registers fit, 96 allow three CTAs, 112 two.  The narrow stages (SA1: 3 -> 64 -> 64 -> 128, 52 KiB of shared memory
+// and 128 TMEM columns per CTA) are bound by the latency of a tile's serial chain, so every additional resident tile
+// is worth more than the walk.  Measured at 32 x 16 384 points: 132 us walking with two CTAs per SM, 112 us with three
+// (a 96-register build of this code), 93 us with four (the 78-register kernel earlier in the round; this 80-register
+// build has not been on a GPU yet -- it differs from the measured 96-register one only in the register cap).
 template <int kMaxReg, bool kWalk>
 __global__ void __maxnreg__(kMaxReg)
 sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
@@ -477,7 +480,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                         // once, where the pooled value is read below.  Four columns per step: two LDS.128 for scale and
                         // shift, two FFMA2, four warp reductions, one 16-byte store of the (uniform) results.
                         if constexpr (!kWalk) {
-                            // three CTAs per SM, 96 registers: 16 independent reductions per accumulator block, each
+                            // narrow build (80 registers): 16 independent reductions per accumulator block, each
                             // lane keeping one of them
                             for (int c0 = 0; c0 < st.n; c0 += 16) {
                                 uint32_t r[16];
@@ -669,10 +672,10 @@ static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false) {
     p.nstages = kTcMaxStages;
     while (p.nstages > 2 && (fixed + p.nstages * p.stage_bytes > limit || (int)p.nstages > total_chunks)) --p.nstages;
     if (dense) {
-        // the deepest ring that does not cost a co-resident CTA (3 is the register-file bound of the kernel)
+        // the deepest ring that does not cost a co-resident CTA (4 is the register-file bound of the narrow build)
         auto ctas = [&](uint32_t ns) {
             const uint32_t per_sm = 228u * 1024u / (fixed + ns * p.stage_bytes + 1024u);
-            return per_sm < 3u ? per_sm : 3u;
+            return per_sm < 4u ? per_sm : 4u;
         };
         p.nstages = kTcMaxStages;
         while (p.nstages > 2 && ctas(p.nstages) < ctas(2)) --p.nstages;
@@ -785,10 +788,10 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     a.cluster = (uint32_t)C;
     if (a.pool_atomic) PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * cout[2] * sizeof(float), stream));
     const int tiles = (a.rows + kTcM - 1) / kTcM;
-    // three CTAs per SM pay off when tiles queue up on every SM and the stage's shared memory allows a third one
-    const int regs = tuning("sa_mlp.regs", 0);  // 0 = auto, else 96 / 168 (A/B measurements)
-    const bool three = regs ? regs == 96 : (tiles > 2 * kNumSMs && (p.smem_bytes + 1024u) * 3u <= 228u * 1024u);
-    auto kernel = three ? sa_mlp_tc_kernel<96, false> : sa_mlp_tc_kernel<168, true>;
+    // the narrow build pays off when tiles queue up on every SM and the stage's shared memory allows three or four CTAs
+    const int regs = tuning("sa_mlp.regs", 0);  // 0 = auto, else 80 / 168 (A/B measurements)
+    const bool narrow = regs ? regs == 80 : (tiles > 2 * kNumSMs && (p.smem_bytes + 1024u) * 3u <= 228u * 1024u);
+    auto kernel = narrow ? sa_mlp_tc_kernel<80, false> : sa_mlp_tc_kernel<168, true>;
     a.probe = g_tc_probe; a.probe_tiles = g_tc_probe_tiles;
     a.relaxed = tiles > kNumSMs && tuning("sa_mlp.backoff", 1) == 1;
     PCST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
@@ -797,7 +800,7 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     // tiles with stride gridDim -- barriers, TMEM and the scale/shift tables are set up once and the weight ring keeps
     // streaming across tile boundaries.  TMEM columns bound the co-residency too (the occupancy API does not know).
     unsigned grid = (unsigned)tiles * C;
-    if (C == 1 && !three && tiles > kNumSMs && tuning("sa_mlp.persistent", 1) == 1) {
+    if (C == 1 && !narrow && tiles > kNumSMs && tuning("sa_mlp.persistent", 1) == 1) {
         // co-resident CTAs per SM from the kernel's own footprint: shared memory (228 KiB per SM at the maximum
         // carve-out, 1 KiB reserved per CTA), registers (64 Ki per SM, allocated per warp in units of 256) and TMEM
         // columns (512 per SM, which the occupancy API does not model)
