@@ -800,7 +800,9 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     // tiles with stride gridDim -- barriers, TMEM and the scale/shift tables are set up once and the weight ring keeps
     // streaming across tile boundaries.  TMEM columns bound the co-residency too (the occupancy API does not know).
     unsigned grid = (unsigned)tiles * C;
-    if (C == 1 && !narrow && tiles > kNumSMs && tuning("sa_mlp.persistent", 1) == 1) {
+    // Plans with N / K halves (layers wider than 256) keep one CTA per tile: their step tables mix partial-sum and pooled
+    // steps mid-sequence, and the walk has only been exercised on GPUs with the plain three-step table.
+    if (C == 1 && !narrow && p.nsteps == 3 && tiles > kNumSMs && tuning("sa_mlp.persistent", 1) == 1) {
         // co-resident CTAs per SM from the kernel's own footprint: shared memory (228 KiB per SM at the maximum
         // carve-out, 1 KiB reserved per CTA), registers (64 Ki per SM, allocated per warp in units of 256) and TMEM
         // columns (512 per SM, which the occupancy API does not model)
