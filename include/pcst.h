@@ -144,8 +144,9 @@ int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_x
                         int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision, int cluster,
                         const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream);
 /* Profiling aid (no reference counterpart): while `stamps` is non-NULL every tensor-core launch records, for each of its
- * first `tiles` 128-row tiles, 16 uint64 in device memory: SM-clock stamps [0] tile start, [1] operand gathered, then per
- * epilogue (accumulator ready, epilogue done); [15] = the SM id.  NULL switches it off. */
+ * first `tiles` 128-row tiles, 16 uint64 in device memory: SM-clock stamps [0] tile start, then per epilogue-bearing step
+ * [2i+1] accumulator ready (gather / previous epilogue + the step's MMAs done) and [2i+2] epilogue done; [15] = the SM id.
+ * NULL switches it off. */
 void pcst_sa_mlp_set_probe(unsigned long long* stamps /*[tiles,16] device*/, int tiles);
 
 /* ---- nearest-neighbour minimum reduction ------------------------------------------------------

@@ -332,7 +332,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
         uint32_t mma_phase = 0, xev = 0;
         for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
             const int row0 = tile * kTcM;
-            // stamps: 0 tile start, 1 operand gathered, then per epilogue (accumulator ready, epilogue done); 15 = SM id
+            // stamps: 0 tile start, then per epilogue-bearing step (accumulator ready, epilogue done); 15 = SM id
             unsigned long long* stamp = (kWalk && a.probe && tid == 0 && rank == 0 && tile < a.probe_tiles) ? a.probe + (size_t)tile * 16 : nullptr;
             int nstamp = 0;
             if (stamp) {
