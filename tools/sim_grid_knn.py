@@ -20,7 +20,7 @@ for _ in (0,):
         uniq, start, cnt = np.unique(keys, return_index=True, return_counts=True)
         cellmap = dict(zip(uniq.tolist(), zip(start.tolist(), cnt.tolist())))
         rs = ref[order]
-        sample = qry[rng.choice(len(qry), 1500, replace=False)]
+        sample = qry[rng.choice(len(qry), int(__import__("os").environ.get("QUERIES", "1500")), replace=False)]
         pairs = []; rings = []; cells_visited = []
         for q in sample:
             qc = np.floor((q - lo) / h).astype(np.int64)
