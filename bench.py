@@ -39,6 +39,17 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def bf16_peak_tflops():
+    """Sustained dense bf16 tensor-core peak for kernels timed inside a step (MEASURED_PEAKS.json), else the
+    profiling recipe's fallback."""
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p.get("bf16_tflops_sustained") or p["bf16_tflops"]), "measured, sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML.  Started before the warm-up (NVML initialisation takes
     longer than a short timed region); only samples taken between begin() and end() -- the timed region -- count."""
@@ -91,28 +102,80 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(inside)}
 
 
+def host_threads() -> int:
+    """Threads the CPU baseline may use: the cores this process is allowed to run on."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle(threads: int):
+    """The CPU oracle port with ALL of its work inside one OpenMP runtime (distance kernels and the shared MLP in
+    oracle/pcst_oracle.c): no second (BLAS / torch) thread pool competes for the cores, which is what slowed the
+    round-1 baseline 2-3x.  An OMP_NUM_THREADS set by a launcher (torchrun exports 1) is overridden explicitly."""
+    from oracle import ref_oracle as O
+
+    O.build()
+    O.set_num_threads(threads)
+    return O
+
+
 def cpu_encoder_baseline(budget_s: float, scan_seed: int = 0):
     """Time the CPU oracle port of the encoder forward on one 120k-point scan (host cores)."""
     import numpy as np
     import torch
-    from oracle import ref_oracle as O
     from pointcloud_style_transfer_b200 import synthetic as S
     from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder
 
-    O.build()
-    O.set_num_threads(os.cpu_count() or 1)
+    O = cpu_oracle(host_threads())
     torch.manual_seed(42)
     sd = {k: v.detach().numpy() for k, v in PointNet2Encoder(feature_dim=FEATURE_DIM).eval().state_dict().items()}
     x = S.lidar_scan(scan_seed).numpy()
     s1, s2 = np.array([1234], np.int64), np.array([99], np.int64)
-    O.encoder_forward(x, sd, s1, s2)  # warm-up
+    O.encoder_forward(x, sd, s1, s2, mlp=O.apply_mlp_c)  # warm-up
     times = []
     t_end = time.perf_counter() + budget_s
     while time.perf_counter() < t_end or len(times) < 3:
         t0 = time.perf_counter()
-        O.encoder_forward(x, sd, s1, s2)
+        O.encoder_forward(x, sd, s1, s2, mlp=O.apply_mlp_c)
         times.append(time.perf_counter() - t0)
     return times, O.num_threads()
+
+
+def cpu_chamfer_knn_baselines():
+    """The other half of the metric on the host cores, bounded samples:
+    Chamfer = the oracle port of chamfer_distance_chunked_optimized on 30k x 30k points of the same two scans
+    (120k x 120k would take ~16x longer: extrapolated pairs/s is the same, the sweep is compute-bound);
+    3-NN = scikit-learn NearestNeighbors(k=3, kd-tree, fp64) on 90 000 queries x 30 000 references, the very call
+    the reference makes at models/diffusion_model.py:146-147 (third-party library, present in this image)."""
+    import numpy as np
+    from pointcloud_style_transfer_b200 import synthetic as S
+
+    O = cpu_oracle(host_threads())
+    out = {}
+    a, b = S.lidar_scan(0, 30000).numpy(), S.lidar_scan(100, 30000).numpy()
+    O.chamfer_distance_chunked_optimized(a[:, :2000], b[:, :2000])
+    t0 = time.perf_counter()
+    O.chamfer_distance_chunked_optimized(a, b)
+    dt = time.perf_counter() - t0
+    out["chamfer"] = {"value": 2.0 * 30000 * 30000 / dt, "unit": "pairs/s", "seconds": dt, "cores": O.num_threads(),
+                      "kind": "port", "sample": "one 30000 x 30000 call of the oracle port of chamfer_distance_chunked_optimized "
+                      "(both directions); the 120k x 120k call is 16x this"}
+    try:
+        from sklearn.neighbors import NearestNeighbors
+        x = S.lidar_scan(2).numpy()[0]
+        perm = np.random.default_rng(0).permutation(x.shape[0])
+        ref, q = x[np.sort(perm[:30000])], x[np.sort(perm[30000:])]
+        t0 = time.perf_counter()
+        NearestNeighbors(n_neighbors=3, algorithm="auto").fit(ref).kneighbors(q)
+        dt = time.perf_counter() - t0
+        out["knn3_90k_x_30k"] = {"value": q.shape[0] / dt, "unit": "queries/s", "seconds": dt, "cores": 1, "kind": "reference",
+                                 "sample": "sklearn NearestNeighbors(n_neighbors=3).fit(30000 pts).kneighbors(90000 pts): the "
+                                 "reference's own call (kd-tree, fp64, single-threaded as the reference leaves n_jobs unset)"}
+    except Exception as e:  # sklearn absent: say so instead of inventing a number
+        out["knn3_90k_x_30k"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def run_reference(args, rank):
@@ -122,22 +185,20 @@ def run_reference(args, rank):
         return
     import numpy as np
     import torch
-    from oracle import ref_oracle as O
     from pointcloud_style_transfer_b200 import synthetic as S
     from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder
 
-    O.build()
-    O.set_num_threads(os.cpu_count() or 1)
+    O = cpu_oracle(host_threads())  # all host threads this process may use, one OpenMP runtime (see cpu_oracle)
     steps = max(1, args.steps)
     torch.manual_seed(42)
     sd = {k: v.detach().numpy() for k, v in PointNet2Encoder(feature_dim=FEATURE_DIM).eval().state_dict().items()}
     x = S.lidar_scan(0).numpy()
     s1, s2 = np.array([1234], np.int64), np.array([99], np.int64)
-    for _ in range(max(0, args.warmup)):
-        O.encoder_forward(x, sd, s1, s2)
+    for _ in range(max(1, args.warmup)):
+        O.encoder_forward(x, sd, s1, s2, mlp=O.apply_mlp_c)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.encoder_forward(x, sd, s1, s2)
+        O.encoder_forward(x, sd, s1, s2, mlp=O.apply_mlp_c)
     dt = (time.perf_counter() - t0) / steps
     value = N_POINTS / dt
     line = {
@@ -145,8 +206,8 @@ def run_reference(args, rank):
         "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "points": N_POINTS, "feature_dim": FEATURE_DIM,
-                   "note": "CPU oracle port of the reference's encoder path (oracle/pcst_oracle.c + numpy MLP); "
-                           "the Python reference cannot travel to the GPU box"},
+                   "note": "CPU oracle port of the reference's encoder path (oracle/pcst_oracle.c, OpenMP, %d threads, "
+                           "no second thread pool); the Python reference cannot travel to the GPU box" % O.num_threads()},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": O.num_threads(), "kind": "port",
                          "sample": f"{steps} full encoder forwards of one 120k-point scan"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,6 +273,11 @@ def main():
     x_dev = scan.to(dev)
     x_host = scan.pin_memory()
     genc = GraphedEncoder(enc)
+    # the same weights on the other shared-MLP path (fp32 and bf16 reported separately)
+    other_precision = 1 - int(bool(args.mlp_precision))
+    enc_other = PointNet2Encoder(feature_dim=FEATURE_DIM, mlp_precision=other_precision).eval().to(dev)
+    enc_other.load_state_dict(enc.state_dict())
+    genc_other = GraphedEncoder(enc_other)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # every rank samples its own GPU; with several ranks on one host poll less often (NVML calls share driver locks)
@@ -255,6 +321,11 @@ def main():
     sampler.end()
     clocks = sampler.stop()
 
+    # ---- the other MLP precision, same scan, same timing recipe ----
+    for _ in range(W):
+        genc_other(x_dev)
+    ms_other = timed(lambda: genc_other(x_dev), K)
+
     # ---- per-op durations (eager, CUDA events around each C-ABI call), for the roofline ----
     torch.cuda.synchronize()
     per_op = {}
@@ -279,6 +350,22 @@ def main():
             chamfer_distance_chunked_optimized(x_dev, y_dev)
         ms_ch = timed(lambda: chamfer_distance_chunked_optimized(x_dev, y_dev), max(1, args.chamfer_steps))
     ch_ms = max(statistics.mean(ms_ch), 1e-9)
+
+    # ---- kNN sweeps (config 5 anchor at N = 1, and the 3-NN of upsample_knn at its product shape) ----
+    knn_ms = {}
+    with torch.no_grad():
+        xq = x_dev[:, :N_POINTS]
+        for name, (q, r, k) in {"knn3_120k_x_120k": (x_dev, y_dev, 3), "knn9_self_120k": (x_dev, x_dev, 9)}.items():
+            for _ in range(2):
+                ops.knn(q, r, k)
+            knn_ms[name] = statistics.mean(timed(lambda: ops.knn(q, r, k), max(1, args.chamfer_steps)))
+        perm = torch.randperm(N_POINTS, generator=torch.Generator().manual_seed(0))
+        r30 = x_dev[:, perm[:30000].sort().values.to(dev)].contiguous()
+        q90 = x_dev[:, perm[30000:].sort().values.to(dev)].contiguous()
+        for _ in range(2):
+            ops.knn(q90, r30, 3)
+        knn_ms["knn3_90k_x_30k"] = statistics.mean(timed(lambda: ops.knn(q90, r30, 3), max(1, args.chamfer_steps)))
+        del xq
 
     # ---- FP32-pipe peak measured in the same run (packed FMA chains on every SM), for the Chamfer roofline ----
     from pointcloud_style_transfer_b200 import _lib
@@ -349,6 +436,8 @@ def main():
     rank_worst = allgather(max(ms_dev))
     rank_mhz = allgather(float(clocks["sm_mhz"]) if clocks["sm_mhz"] is not None else -1.0)
     rank_throttled = allgather(float(len([r for r in clocks["reasons"] if not r.startswith("nvml_unavailable")])))
+    rank_median = allgather(statistics.median(ms_dev))
+    t_other = allmax(sum(ms_other)) / K
     t_dev = allmax(sum(ms_dev)) / K          # ms per step, max over ranks
     t_e2e = allmax(sum(ms_e2e)) / K
     t_ch = allmax(ch_ms)
@@ -367,6 +456,39 @@ def main():
         fp32_peak = fp32_measured or fp32_nominal
         # one sweep serves both directions (the second matrix is the exact transpose): N*M unique pair evaluations
         ch_tflops = 8.0 * (pairs / 2) / (t_ch * 1e-3) / 1e12
+        # ---- per-kernel rooflines from the eager CUDA-event durations of this run (SURVEY.md 8(d) work per unit) ----
+        def call_ms(name, i):
+            return statistics.mean(v[i] for v in per_op[name] if len(v) > i)
+
+        bf16_peak, bf16_src = bf16_peak_tflops()
+        mlp_rows = [NPOINT1 * 32, 128 * 64, 128]
+        mlp_macs = [3 * 64 + 64 * 64 + 64 * 128, 131 * 128 + 128 * 128 + 128 * 256, 259 * 256 + 256 * 512 + 512 * FEATURE_DIM]
+        tc = args.mlp_precision == 1
+        kernels = []
+        for i, stage in enumerate(("SA1", "SA2", "SA3 (group_all)")):
+            ms = call_ms("pcst_sa_mlp_max_f32", i)
+            tf = 2.0 * mlp_rows[i] * mlp_macs[i] / (ms * 1e-3) / 1e12
+            peak = bf16_peak if tc else fp32_peak
+            kernels.append({"kernel": ("sa_mlp_tc_kernel " if tc else "mlp_layer_kernel ") + stage, "bound": "tensor" if tc else "fp32",
+                            "ms": ms, "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                            "work": "2 * rows * sum(Cin * Cout) = %.3f GFLOP (%d rows)" % (2e-9 * mlp_rows[i] * mlp_macs[i], mlp_rows[i]),
+                            "note": "one scan is a few microseconds of tensor work: latency-bound at this shape; "
+                                    "the batched shape is under `train_c4` / profiles"})
+        bq_ms = call_ms("pcst_ball_query_f32", 1)
+        bq_tf = 8.0 * NPOINT1 * N_POINTS / (bq_ms * 1e-3) / 1e12
+        kernels.append({"kernel": "bq_mask_kernel + bq_emit_kernel (SA1 ball query, 512 x 120000 full sweep)", "bound": "fp32",
+                        "ms": bq_ms, "achieved": bq_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": bq_tf / fp32_peak,
+                        "work": "8 flop per (query, candidate) pair of the full S x N sweep = 0.49 GFLOP"})
+        kernels.append({"kernel": "fps_kernel (SA2, 512 -> 128, one CTA)", "bound": "latency", "ms": call_ms("pcst_fps_f32", 1),
+                        "ns_per_iteration": call_ms("pcst_fps_f32", 1) * 1e6 / 128, "note": "on a parallel graph branch"})
+        kernels.append({"kernel": "bq_small_kernel (SA2 ball query, 128 x 512)", "bound": "latency", "ms": call_ms("pcst_ball_query_f32", 0)})
+        for name, (nq, nr, kk) in {"knn3_90k_x_30k": (90000, 30000, 3), "knn3_120k_x_120k": (N_POINTS, N_POINTS, 3),
+                                   "knn9_self_120k": (N_POINTS, N_POINTS, 9)}.items():
+            tf = 8.0 * nq * nr / (knn_ms[name] * 1e-3) / 1e12
+            kernels.append({"kernel": "knn (%s, k=%d, fp64-exact ranking)" % (name, kk), "bound": "fp32", "ms": knn_ms[name],
+                            "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                            "work": "8 flop per pair of the brute-force sweep (%d x %d); a search that visits fewer pairs can exceed 1" % (nq, nr)})
+
         line = {
             "metric": "SA points/sec (PointNet2Encoder fwd, 120k-pt scan)", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_dev, "higher_is_better": True,
@@ -387,6 +509,15 @@ def main():
                          "peak_source": peak_src, "kernel_ms": fps_ms_max,
                          "model": "streaming-model bytes npoint*N*20 B per launch (SURVEY.md 8(d)): what an FPS that re-reads xyz and "
                                   "running distances every iteration moves; the kernel is bound by its 512 serial cluster exchanges"},
+            "mlp_precisions": {("bf16_tcgen05" if args.mlp_precision == 1 else "fp32_cuda_core"): {"ms_per_step": t_dev, "value": value},
+                               ("fp32_cuda_core" if args.mlp_precision == 1 else "bf16_tcgen05"):
+                                   {"ms_per_step": t_other, "value": world * N_POINTS / (t_other * 1e-3)},
+                               "note": "same scan, weights and timing recipe; the headline `value` is the first entry"},
+            "fps": {"ns_per_iteration": fps_ms_max * 1e6 / NPOINT1, "iterations": NPOINT1,
+                    "note": "the honest figure for this latency-bound kernel: one iteration = one 16-CTA cluster exchange"},
+            "kernels": kernels,
+            "kernels_note": "eager CUDA-event duration around each C-ABI call (includes launch gaps for microsecond-scale kernels); "
+                            "ncu per-launch durations of the same kernels are under profiles/",
             "op_ms_eager": op_ms,
             "chamfer": {"metric": "Chamfer NN pairs/sec (120k x 120k, both directions)", "value": world * pairs / (t_ch * 1e-3),
                         "unit": "pairs/s", "ms_per_call": t_ch,
@@ -398,7 +529,7 @@ def main():
                                      "peak_source": "measured in this run" if fp32_measured else "computed",
                                      "frac_if_both_directions_counted": 2 * ch_tflops / fp32_peak}},
             "clocks": clocks,
-            "ranks": {"ms_per_step": rank_ms, "slowest_single_step_ms": rank_worst, "sm_mhz": rank_mhz,
+            "ranks": {"ms_per_step": rank_ms, "median_step_ms": rank_median, "slowest_single_step_ms": rank_worst, "sm_mhz": rank_mhz,
                       "throttle_reasons_seen": rank_throttled},
         }
         if t_b is not None:
@@ -416,10 +547,14 @@ def main():
                 "value": N_POINTS * float(N_POINTS) / (t_knn * 1e-3), "unit": "pairs/s", "ms_per_call": t_knn,
                 "scaling": "strong", "collectives": "all-gather of the reference cloud (1.44 MB); results stay sharded"}
         if not args.no_cpu_baseline and world == 1:
-            times, cores = cpu_encoder_baseline(budget_s=10.0)
+            times, cores = cpu_encoder_baseline(budget_s=8.0)
             line["cpu_baseline"] = {"value": N_POINTS / statistics.mean(times), "unit": "points/s", "cores": cores,
                                     "kind": "port", "sample": f"{len(times)} encoder forwards of the same 120k-point scan "
-                                    "by the CPU oracle (C + numpy), ~10 s"}
+                                    "by the CPU oracle (C, one OpenMP runtime, %d threads), ~8 s" % cores,
+                                    "best_ms": min(times) * 1e3, "mean_ms": statistics.mean(times) * 1e3}
+            other = cpu_chamfer_knn_baselines()
+            line["chamfer"]["cpu_baseline"] = other["chamfer"]
+            line["knn_cpu_baseline"] = other["knn3_90k_x_30k"]
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -21,7 +21,9 @@
  *    matching *_workspace_bytes() function.  ws must be 256-byte aligned.
  *  - Kernels are launched on the cudaStream_t passed as `stream` (a void* here so that the header
  *    needs no CUDA include); calls are stream-ordered, asynchronous and re-entrant.  There are no
- *    implicit device synchronisations and no host<->device copies.
+ *    implicit device synchronisations and no host<->device copies.  The only process-wide mutable
+ *    state is the tuning-knob table (pcst_set_tuning, mutex-guarded) and the profiling hook
+ *    pcst_sa_mlp_set_probe, both of which exist for measurements and default to "off".
  *  - There is no CPU fallback.  On a device that is not compute capability 10.x every compute
  *    entry point returns PCST_ERR_UNSUPPORTED.
  */

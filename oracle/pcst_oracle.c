@@ -262,3 +262,60 @@ void oracle_knn(const float* query, const float* ref, int B, int Q, int R, int k
         }
     }
 }
+
+/* ---- SetAbstraction.apply_mlp: models/pointnet2_encoder.py:106-112 (eval-mode BatchNorm) ----------
+ * x [G*K, C0] (row = one grouped point, channels last), three layers relu(bn(conv1x1(.))), then the
+ * max over each group's K rows (torch.max(points, 3)[0], :112) -> out [G, C3].
+ * wt[l] is the conv weight TRANSPOSED to [Cin_l, Cout_l] (so that the inner loop runs over output
+ * channels and vectorises without re-association); bias/gamma/beta/mean/var [Cout_l].
+ * Arithmetic: z = sum_ci x[ci] * w[co,ci] (sequential over ci, separate multiply and add) + bias;
+ * y = (z - mean) / sqrt(var + eps) * gamma + beta; relu.  Differs from MKL's blocked summation only
+ * in rounding (tests: rtol 1e-4).  Used by bench.py's CPU baseline so that the whole encoder runs in
+ * ONE OpenMP runtime (no OpenMP x BLAS thread-pool oversubscription). */
+void oracle_apply_mlp3(const float* x, long G, int K, int C0, const int* cout, const float* const* wt,
+                       const float* const* bias, const float* const* gamma, const float* const* beta,
+                       const float* const* mean, const float* const* var, float eps, float* out) {
+    const int C1 = cout[0], C2 = cout[1], C3 = cout[2];
+    int cmax = C1 > C2 ? C1 : C2;
+    if (C3 > cmax) cmax = C3;
+    if (C0 > cmax) cmax = C0;
+    float* inv[3];
+    for (int l = 0; l < 3; ++l) {
+        inv[l] = (float*)malloc(sizeof(float) * (size_t)cout[l]);
+        for (int c = 0; c < cout[l]; ++c) inv[l][c] = sqrtf(var[l][c] + eps);
+    }
+#pragma omp parallel
+    {
+        float* a = (float*)malloc(sizeof(float) * (size_t)cmax);
+        float* z = (float*)malloc(sizeof(float) * (size_t)cmax);
+#pragma omp for schedule(static)
+        for (long g = 0; g < G; ++g) {
+            float* o = out + (size_t)g * C3;
+            for (int k = 0; k < K; ++k) {
+                const float* row = x + ((size_t)g * K + k) * C0;
+                int cin = C0;
+                for (int c = 0; c < C0; ++c) a[c] = row[c];
+                for (int l = 0; l < 3; ++l) {
+                    const int co_n = cout[l];
+                    const float* w = wt[l];
+                    for (int co = 0; co < co_n; ++co) z[co] = 0.f;
+                    for (int ci = 0; ci < cin; ++ci) {
+                        const float xv = a[ci];
+                        const float* wr = w + (size_t)ci * co_n;
+                        for (int co = 0; co < co_n; ++co) z[co] += xv * wr[co];
+                    }
+                    for (int co = 0; co < co_n; ++co) {
+                        float y = (z[co] + bias[l][co] - mean[l][co]) / inv[l][co] * gamma[l][co] + beta[l][co];
+                        a[co] = y > 0.f ? y : 0.f;
+                    }
+                    cin = co_n;
+                }
+                if (k == 0) for (int c = 0; c < C3; ++c) o[c] = a[c];
+                else for (int c = 0; c < C3; ++c) o[c] = a[c] > o[c] ? a[c] : o[c];
+            }
+        }
+        free(a);
+        free(z);
+    }
+    for (int l = 0; l < 3; ++l) free(inv[l]);
+}

@@ -127,6 +127,33 @@ def apply_mlp(points, layers: Sequence[Dict[str, np.ndarray]], eps: float = 1e-5
     return np.ascontiguousarray(x.max(axis=2).transpose(0, 2, 1))
 
 
+def apply_mlp_c(points, layers: Sequence[Dict[str, np.ndarray]], eps: float = 1e-5) -> np.ndarray:
+    """``apply_mlp`` evaluated by the C oracle (``oracle_apply_mlp3``, OpenMP over groups) instead of numpy/BLAS:
+    same formula, sequential summation.  bench.py's CPU baseline uses it so that the whole encoder runs inside ONE
+    OpenMP runtime (an OpenMP pool next to a BLAS pool oversubscribes the cores and slows both)."""
+    x = _f32(points)
+    B, S, K, C0 = x.shape
+    assert len(layers) == 3
+    fp = ctypes.POINTER(ctypes.c_float)
+    keep = []
+
+    def arr(key, transpose=False):
+        vals = []
+        for L in layers:
+            v = _f32(L[key])
+            if transpose:
+                v = np.ascontiguousarray(v.reshape(v.shape[0], -1).T)
+            vals.append(v)
+        keep.append(vals)
+        return (fp * 3)(*[_ptr(v, fp) for v in vals])
+
+    cout = (ctypes.c_int * 3)(*[int(L["weight"].shape[0]) for L in layers])
+    out = np.empty((B * S, cout[2]), np.float32)
+    lib().oracle_apply_mlp3(_ptr(x, fp), ctypes.c_long(B * S), int(K), int(C0), cout, arr("weight", True), arr("bias"),
+                            arr("gamma"), arr("beta"), arr("mean"), arr("var"), ctypes.c_float(eps), _ptr(out, fp))
+    return np.ascontiguousarray(out.reshape(B, S, -1).transpose(0, 2, 1))
+
+
 def layers_from_state_dict(sd: Dict[str, np.ndarray], prefix: str) -> list:
     """Collect ``{prefix}mlp_convs.i.*`` / ``{prefix}mlp_bns.i.*`` (models/pointnet2_encoder.py:68-75)."""
     out, i = [], 0
@@ -141,11 +168,13 @@ def layers_from_state_dict(sd: Dict[str, np.ndarray], prefix: str) -> list:
     return out
 
 
-def set_abstraction(xyz, points, layers, npoint, radius, nsample, start, group_all=False):
+def set_abstraction(xyz, points, layers, npoint, radius, nsample, start, group_all=False, mlp=None):
     """SetAbstraction.forward, models/pointnet2_encoder.py:78-104 (eval mode).
 
     Returns (new_xyz [B,S,3], new_points [B,C_out,S] or [B,C_out] for group_all, fps_idx, group_idx).
+    ``mlp`` = ``apply_mlp`` (numpy, default) or ``apply_mlp_c``.
     """
+    apply_mlp = mlp or globals()["apply_mlp"]
     xyz = _f32(xyz)
     B, N, _ = xyz.shape
     if group_all:
@@ -163,17 +192,17 @@ def set_abstraction(xyz, points, layers, npoint, radius, nsample, start, group_a
     return new_xyz, apply_mlp(g, layers), fps_idx, group_idx
 
 
-def encoder_forward(xyz, sd: Dict[str, np.ndarray], start1, start2) -> Dict[str, np.ndarray]:
+def encoder_forward(xyz, sd: Dict[str, np.ndarray], start1, start2, mlp=None) -> Dict[str, np.ndarray]:
     """PointNet2Encoder.forward, models/pointnet2_encoder.py:114-131 (eval mode).
 
     ``start1`` / ``start2`` are the FPS start indices of sa1 / sa2 (two consecutive
     ``torch.randint`` draws on the CPU generator in the reference, :36).
     """
-    l1_xyz, l1_pts, f1, g1 = set_abstraction(xyz, None, layers_from_state_dict(sd, "sa1."), 512, 0.2, 32, start1)
+    l1_xyz, l1_pts, f1, g1 = set_abstraction(xyz, None, layers_from_state_dict(sd, "sa1."), 512, 0.2, 32, start1, mlp=mlp)
     l2_xyz, l2_pts, f2, g2 = set_abstraction(l1_xyz, l1_pts.transpose(0, 2, 1), layers_from_state_dict(sd, "sa2."),
-                                             128, 0.4, 64, start2)
+                                             128, 0.4, 64, start2, mlp=mlp)
     _, g, _, _ = set_abstraction(l2_xyz, l2_pts.transpose(0, 2, 1), layers_from_state_dict(sd, "sa3."),
-                                 None, None, None, None, group_all=True)
+                                 None, None, None, None, group_all=True, mlp=mlp)
     return dict(feature=g, l1_xyz=l1_xyz, l1_points=l1_pts, l2_xyz=l2_xyz, l2_points=l2_pts,
                 fps1=f1, fps2=f2, group1=g1, group2=g2)
 

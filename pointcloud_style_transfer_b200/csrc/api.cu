@@ -25,6 +25,21 @@ int check_cuda(cudaError_t e, const char* what) {
     return PCST_ERR_CUDA;
 }
 
+int num_sms() {
+    static thread_local int cached_dev = -2, cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();  // no device (plan queries on a build host): the B200 value
+        return 148;
+    }
+    if (dev != cached_dev) {
+        int n = 0;
+        cached = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
 static std::mutex g_tune_mu;
 static std::map<std::string, int>& tune_map() {
     static std::map<std::string, int> m = {
@@ -94,7 +109,7 @@ fp32_probe_kernel(int iters, float* __restrict__ out) {
 
 int launch_pack(const float* xyz, int B, int N, int Npad, float4* out, cudaStream_t stream) {
     int blocks = (Npad + 255) / 256;
-    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     pack_points_kernel<<<dim3(blocks, B), 256, 0, stream>>>(xyz, N, Npad, out);
     return check_cuda(cudaGetLastError(), "pack_points_kernel");
 }
@@ -132,7 +147,7 @@ int pcst_l2_prefetch(const void* ptr, size_t bytes, pcst_stream_t stream_) {
 
 long long pcst_fp32_probe(int iters, float* scratch, pcst_stream_t stream_) {
     if (iters <= 0 || !scratch) return 0;
-    const int blocks = 8 * pcst::kNumSMs, threads = 256;
+    const int blocks = 8 * pcst::num_sms(), threads = 256;
     pcst::fp32_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream_>>>(iters, scratch);
     if (cudaGetLastError() != cudaSuccess) return 0;
     return (long long)blocks * threads * 8 * 2 * 2 * iters;  // 8 chains x 2 lanes x (mul + add) per iteration

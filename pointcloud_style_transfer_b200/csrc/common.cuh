@@ -13,7 +13,9 @@
 
 namespace pcst {
 
-constexpr int kNumSMs = 148;  // B200; grids are sized in multiples of this
+// SM count of the current device (148 on a B200), queried once per device; grids are sized in multiples of it.
+// Host-only plan queries on a machine without a GPU get the B200 value.
+int num_sms();
 
 // ---- host-side error plumbing --------------------------------------------------------------
 void set_error(const char* fmt, ...);

@@ -296,7 +296,7 @@ static FpsPlan fps_plan(int B, int N) {
     // a batch that would need more than one wave of clusters: an iteration costs about the same for any cluster
     // size (it is the exchange chain), so prefer smaller clusters as long as the cloud still fits their registers
     if (tuning("fps.cluster", 0) == 0)
-        while (C > 1 && (long)B * C > kNumSMs && (long)N <= (long)(C / 2) * kFpsMaxThreads * 16) C /= 2;
+        while (C > 1 && (long)B * C > num_sms() && (long)N <= (long)(C / 2) * kFpsMaxThreads * 16) C /= 2;
     p.C = C;
     int threads = tuning("fps.threads", 0);
     // measured (B200, 512 -> 128): 128 threads 63 us, 32 threads 72 us, 512 threads 65 us per launch

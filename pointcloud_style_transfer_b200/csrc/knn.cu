@@ -211,7 +211,7 @@ using namespace pcst;
 static int knn_splits(int B, int Q, int R) {
     const long ctas = (long)B * ((Q + kKnnThreads - 1) / kKnnThreads);
     const int tiles = (R + kKnnTile - 1) / kKnnTile;
-    long s = (2L * kNumSMs + ctas - 1) / ctas;
+    long s = (2L * num_sms() + ctas - 1) / ctas;
     if (s > tiles) s = tiles;
     if (s > 64) s = 64;
     return s < 1 ? 1 : (int)s;

@@ -562,7 +562,7 @@ static NNPlan make_plan(int B, int N, int M, int R = 4) {
     p.row_tiles = (N + rows_per_cta - 1) / rows_per_cta;
     const int cand_tiles = p.Mpad / kTilePoints;
     // choose the number of candidate splits that best fills whole waves of 2 CTAs/SM x 148 SMs
-    const long wave = 2L * kNumSMs;
+    const long wave = 2L * num_sms();
     int forced = tuning("nn_min.splits", 0);
     int best_s = 1;
     double best_eff = -1.0;
@@ -786,7 +786,7 @@ extern "C" int pcst_chamfer_bwd_f32(const float* pred, const float* target, cons
     PCST_CUDA(cudaMemsetAsync(grad_pred, 0, (size_t)B * N * 3 * sizeof(float), stream));
     PCST_CUDA(cudaMemsetAsync(grad_target, 0, (size_t)B * M * 3 * sizeof(float), stream));
     int blocks = (N + M + 255) / 256;
-    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
     chamfer_bwd_kernel<<<dim3(blocks, B), 256, 0, stream>>>(pred, target, arg_pt, arg_tp, grad_out, N, M, grad_pred,
                                                              grad_target);
     return check_cuda(cudaGetLastError(), "chamfer_bwd_kernel");

@@ -193,6 +193,12 @@ __global__ void tc_pack_ss_kernel(const float* __restrict__ scale, const float* 
     }
 }
 
+// Stream-ordered boundary after a pack.  sa_mlp_tc_kernel is launched with programmatic stream serialization and reads
+// the packed blob (weights by TMA, the scale/shift tables) BEFORE its griddepcontrol.wait, which is only safe when the
+// blob's writers are not its immediate predecessor in the stream: this empty, ordinarily-launched kernel starts after the
+// pack kernels have completed (and flushed), and it is the kernel a following PDL launch may overlap with.
+__global__ void tc_pack_fence_kernel() {}
+
 // Two instantiations.  <168, true>: CTAs walk several row tiles when there are more tiles than the machine holds (two
 // CTAs per SM; barriers, TMEM and the scale/shift tables set up once, the weight ring streaming across tile boundaries).
 // <80, false>: one tile per CTA within the register budget that lets FOUR CTAs share an SM.  A CTA's six warps land
@@ -718,7 +724,7 @@ bool sa_mlp_tc_supported(int D, const int* cout) { return tc_plan(D, cout, 1).ok
 int sa_mlp_tc_pick_cluster(long tiles, int D, const int* cout) {
     int best = 1;
     for (int C = 2; C <= 8; C *= 2)
-        if (tiles * C <= kNumSMs && tc_plan(D, cout, C).ok) best = C;
+        if (tiles * C <= num_sms() && tc_plan(D, cout, C).ok) best = C;
     return best;
 }
 size_t sa_mlp_tc_blob_bytes(int D, const int* cout, int C) {
@@ -751,6 +757,8 @@ int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, int C, void* blob, cudaStream_
         PCST_CUDA(cudaGetLastError());
         at += p.n[l];
     }
+    tc_pack_fence_kernel<<<1, 32, 0, stream>>>();
+    PCST_CUDA(cudaGetLastError());
     return PCST_OK;
 }
 
@@ -764,7 +772,7 @@ void sa_mlp_tc_set_probe(unsigned long long* buf, int tiles) {
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
                   int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream) {
     const size_t rows_sz = (size_t)B * S * K;
-    const TcPlan p = tc_plan(D, cout, C, /*dense=*/(rows_sz + kTcM - 1) / kTcM > (size_t)2 * kNumSMs);
+    const TcPlan p = tc_plan(D, cout, C, /*dense=*/(rows_sz + kTcM - 1) / kTcM > (size_t)2 * num_sms());
     if (!p.ok) {
         set_error("sa_mlp_max (tensor-core path): unsupported layer widths / cluster size");
         return PCST_ERR_UNSUPPORTED;
@@ -790,10 +798,10 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     const int tiles = (a.rows + kTcM - 1) / kTcM;
     // the narrow build pays off when tiles queue up on every SM and the stage's shared memory allows three or four CTAs
     const int regs = tuning("sa_mlp.regs", 0);  // 0 = auto, else 80 / 168 (A/B measurements)
-    const bool narrow = regs ? regs == 80 : (tiles > 2 * kNumSMs && (p.smem_bytes + 1024u) * 3u <= 228u * 1024u);
+    const bool narrow = regs ? regs == 80 : (tiles > 2 * num_sms() && (p.smem_bytes + 1024u) * 3u <= 228u * 1024u);
     auto kernel = narrow ? sa_mlp_tc_kernel<80, false> : sa_mlp_tc_kernel<168, true>;
     a.probe = g_tc_probe; a.probe_tiles = g_tc_probe_tiles;
-    a.relaxed = tiles > kNumSMs && tuning("sa_mlp.backoff", 1) == 1;
+    a.relaxed = tiles > num_sms() && tuning("sa_mlp.backoff", 1) == 1;
     PCST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     a.ntiles = tiles;
     // More tiles than the machine holds at once (C == 1 by construction): as many CTAs as are co-resident, each walking
@@ -802,7 +810,7 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     unsigned grid = (unsigned)tiles * C;
     // Plans with N / K halves (layers wider than 256) keep one CTA per tile: their step tables mix partial-sum and pooled
     // steps mid-sequence, and the walk has only been exercised on GPUs with the plain three-step table.
-    if (C == 1 && !narrow && p.nsteps == 3 && tiles > kNumSMs && tuning("sa_mlp.persistent", 1) == 1) {
+    if (C == 1 && !narrow && p.nsteps == 3 && tiles > num_sms() && tuning("sa_mlp.persistent", 1) == 1) {
         // co-resident CTAs per SM from the kernel's own footprint: shared memory (228 KiB per SM at the maximum
         // carve-out, 1 KiB reserved per CTA), registers (64 Ki per SM, allocated per warp in units of 256) and TMEM
         // columns (512 per SM, which the occupancy API does not model)
@@ -813,7 +821,7 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
         if (occ > 65536 / regs_per_cta) occ = 65536 / regs_per_cta;
         if (occ > 512 / (int)p.tmem_cols) occ = 512 / (int)p.tmem_cols;
         if (occ < 1) occ = 1;
-        if ((unsigned)(occ * kNumSMs) < grid) grid = (unsigned)(occ * kNumSMs);
+        if ((unsigned)(occ * num_sms()) < grid) grid = (unsigned)(occ * num_sms());
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

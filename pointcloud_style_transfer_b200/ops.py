@@ -52,7 +52,7 @@ def _workspace(nbytes: int, device) -> Tensor:
 # roofline's live kernel durations).  KERNELS_PER_CALL counts __global__ launches (memsets excluded).
 KERNELS_PER_CALL = {"pcst_l2_prefetch": 1, "pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
-                    "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 7, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_nn_min_pair_arg_f32": 6, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
+                    "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 8, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_nn_min_pair_arg_f32": 6, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
                     "pcst_knn_interpolate_f32": 1, "pcst_minmax_f32": 1, "pcst_voxel_representatives_f32": 2}
 launch_count = 0
 _event_log = None  # None = off; else list of (name, start_event, end_event)
@@ -484,8 +484,11 @@ def knn(query: Tensor, ref: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     idx = torch.empty(B, Q, k, dtype=torch.int64, device=query.device)
     dist = torch.empty(B, Q, k, dtype=torch.float64, device=query.device)
     with torch.cuda.device(query.device):
-        ws = _workspace(lib.pcst_knn_workspace_bytes(B, Q, R, k), query.device)
-        _call("pcst_knn_f32", _p(query), _p(ref), B, Q, R, k, _p(idx), _p(dist), _p(ws), ws.numel(), _stream())
+        nb = lib.pcst_knn_workspace_bytes(B, Q, R, k)
+        ws = _workspace(nb, query.device)
+        # a non-empty workspace = the reference range is split over CTAs: sweep + merge kernel
+        _call("pcst_knn_f32", _p(query), _p(ref), B, Q, R, k, _p(idx), _p(dist), _p(ws), ws.numel(), _stream(),
+              kernels=2 if nb > 0 else 1)
     return dist, idx
 
 

@@ -250,6 +250,79 @@ def test_encoder_120k_against_oracle(api, dev, oracle, golden):
     np.testing.assert_allclose(feat, ref["feature"], rtol=1e-4, atol=1e-5)
 
 
+def test_encoder_120k_bf16_benchmarked_config_against_oracle(api, dev, oracle, golden):
+    """The configuration bench.py times (BASELINE config 2): ONE 120 000-point LiDAR scan, F = 256, shared MLPs on
+    the bf16 tcgen05 path (precision 1).  Indices are precision-independent (bit-exact tests above); the feature is
+    compared with the oracle's fp32 restatement of models/pointnet2_encoder.py:114-131 at the stated bf16 tolerance
+    rtol 2e-2 / atol 2e-2, and the error must be bf16-sized (not garbage that happens to sit inside atol)."""
+    g, enc = load_encoder(api, golden, dev, precision=1)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    for scan_seed, rng_seed in ((0, 7), (3, 11)):
+        x = S.lidar_scan(scan_seed)
+        torch.manual_seed(rng_seed)
+        s1 = torch.randint(0, 120000, (1,), dtype=torch.long).numpy()
+        s2 = torch.randint(0, 512, (1,), dtype=torch.long).numpy()
+        torch.manual_seed(rng_seed)
+        with torch.no_grad():
+            feat = enc(x.to(dev)).cpu().numpy()
+        ref = oracle.encoder_forward(x.numpy(), sd, s1, s2)["feature"]
+        assert feat.shape == (1, 256)
+        np.testing.assert_allclose(feat, ref, rtol=2e-2, atol=2e-2)
+        err = np.abs(feat - ref).max() / np.abs(ref).max()
+        assert err < 1e-2, err
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_graphed_encoder_120k_equals_eager_both_precisions(api, dev, golden, precision):
+    """bench.py times runtime.GraphedEncoder: the graph replay (device-resident input and the pinned-host path of the
+    end-to-end number) must return exactly what the eager forward of the same precision returns."""
+    from pointcloud_style_transfer_b200.runtime import GraphedEncoder
+
+    g, enc = load_encoder(api, golden, dev, precision=precision)
+    genc = GraphedEncoder(enc)
+    x = S.lidar_scan(1)
+    xd = x.to(dev)
+    for seed in (1234, 5):
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            eager = enc(xd).clone()
+        torch.manual_seed(seed)
+        assert torch.equal(eager, genc(xd).clone())
+        torch.manual_seed(seed)
+        assert torch.equal(eager, genc(x.pin_memory()).clone())
+
+
+def test_graphed_encoder_recaptures_when_parameters_or_precision_change(api, dev, golden):
+    """The captured graph bakes in pointers to the packed weight blobs: a parameter update, load_state_dict or a
+    precision switch must invalidate it (stale weights / freed blobs on replay)."""
+    from pointcloud_style_transfer_b200.runtime import GraphedEncoder
+
+    g, enc = load_encoder(api, golden, dev, precision=1)
+    genc = GraphedEncoder(enc)
+    x = torch.from_numpy(g["x"]).to(dev)
+    torch.manual_seed(3)
+    a = genc(x).clone()
+    with torch.no_grad():
+        enc.sa3.mlp_convs[2].weight.mul_(0.5)          # in-place update = optimizer.step()
+        enc.sa1.mlp_bns[0].running_var.add_(0.25)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        eager = enc(x).clone()
+    torch.manual_seed(3)
+    b = genc(x).clone()
+    assert torch.equal(b, eager) and not torch.equal(a, b)
+    enc.set_mlp_precision(0)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        eager0 = enc(x).clone()
+    torch.manual_seed(3)
+    assert torch.equal(genc(x).clone(), eager0)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    enc.load_state_dict(sd, strict=False)
+    torch.manual_seed(1234)
+    np.testing.assert_allclose(genc(x).cpu().numpy(), g["feature"], rtol=1e-4, atol=1e-5)
+
+
 def test_encoder_bf16_tensor_core_path(api, dev, golden):
     """precision 1: SA1 / SA2 MLPs on tcgen05 (bf16 operands, fp32 accumulate).  Indices are untouched by
     the precision switch; features within the stated bf16 tolerance rtol 2e-2 / atol 2e-2."""
@@ -632,6 +705,58 @@ def test_knn_matches_oracle(api, dev, oracle, k):
     rd, ri = oracle.knn(q, r, k)
     assert np.array_equal(idx.cpu().numpy(), ri)
     assert np.array_equal(dist.cpu().numpy(), rd)  # fp64, same operation order -> identical
+
+
+def _knn_subset_check(api, dev, oracle, q, r, k, rows):
+    """Full-size search on the GPU; the oracle (fp64 brute force, sklearn's order) re-does a row subset."""
+    dist, idx = api.ops.knn(torch.from_numpy(q).to(dev), torch.from_numpy(r).to(dev), k)
+    dist, idx = dist.cpu().numpy(), idx.cpu().numpy()
+    rd, ri = oracle.knn(np.ascontiguousarray(q[:, rows]), r, k)
+    assert np.array_equal(idx[:, rows], ri)
+    assert np.array_equal(dist[:, rows], rd)
+    assert (np.diff(dist, axis=-1) >= 0).all()          # ascending everywhere, not only on the subset
+    assert (idx >= 0).all() and (idx < r.shape[1]).all()
+    return dist, idx
+
+
+def test_knn_full_size_upsample_shape_90k_x_30k(api, dev, oracle):
+    """The 3-NN of upsample_knn at the product shape (models/diffusion_model.py:143-147): 90 000 unknown points of a
+    120k LiDAR scan against its 30 000 known ones; 2 048 query rows re-done by the oracle, bit-identical."""
+    x = S.lidar_scan(2).numpy()[0]
+    perm = np.random.default_rng(0).permutation(120000)
+    r, q = x[np.sort(perm[:30000])][None], x[np.sort(perm[30000:])][None]
+    rows = np.random.default_rng(1).choice(90000, 2048, replace=False)
+    _knn_subset_check(api, dev, oracle, q, r, 3, np.sort(rows))
+
+
+def test_knn_full_size_self_9nn_120k(api, dev, oracle):
+    """uniformity_score's search (evaluation/metrics.py:152-153): 9-NN self query on a 120k scan; column 0 is the
+    point itself at distance 0."""
+    x = S.lidar_scan(4).numpy()
+    rows = np.sort(np.random.default_rng(2).choice(120000, 2048, replace=False))
+    dist, idx = _knn_subset_check(api, dev, oracle, x, x, 9, rows)
+    assert (dist[..., 0] == 0).all()
+
+
+def test_upsample_knn_full_size_against_oracle_subset(api, dev, oracle):
+    """HierarchicalProcessor.upsample_knn at 120k -> known 30k: interpolated values of a 4 096-point slice equal the
+    oracle's (which needs only those rows' neighbours)."""
+    hp = api.dm.HierarchicalProcessor(120000, 30000)
+    x = S.lidar_scan(5)
+    idx = torch.from_numpy(np.sort(np.random.default_rng(3).permutation(120000)[:30000]))[None]
+    coarse = torch.randn(1, 30000, 3, generator=torch.Generator().manual_seed(9))
+    out = hp.upsample_knn(coarse.to(dev), x.to(dev), idx.to(dev)).cpu().numpy()
+    assert out.shape == (1, 120000, 3)
+    known = np.zeros(120000, bool)
+    known[idx[0].numpy()] = True
+    assert np.array_equal(out[0, idx[0].numpy()], coarse[0].numpy())
+    unk = np.nonzero(~known)[0][:4096]
+    fit = x.numpy()[0][idx[0].numpy()]
+    rd, ri = oracle.knn(x.numpy()[:, unk], fit[None], 3)
+    w = 1.0 / (rd[0] + 1e-8)
+    w = w / w.sum(axis=1, keepdims=True)
+    ref = np.sum(coarse[0].numpy()[ri[0]] * w[..., None], axis=1).astype(np.float32)
+    np.testing.assert_allclose(out[0, unk], ref, rtol=1e-6, atol=1e-7)
 
 
 def test_upsample_knn_golden(api, dev, golden, oracle):
