@@ -151,6 +151,54 @@ int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_x
  * NULL switches it off. */
 void pcst_sa_mlp_set_probe(unsigned long long* stamps /*[tiles,16] device*/, int tiles);
 
+/* ---- SetAbstraction.apply_mlp in TRAINING mode: models/pointnet2_encoder.py:74,106-112 under module.train() --------
+ * (the step of training/trainer.py:78-117 that the reference runs through cuDNN / cuBLAS + autograd)
+ * Same fused grouping gather as pcst_sa_mlp_max_f32, but nn.BatchNorm2d uses BATCH statistics over all B*S*K rows
+ * (biased variance, eps inside the square root), updates running_mean / running_var (momentum, unbiased variance) and
+ * num_batches_tracked in place, and the backward returns the gradients autograd would.
+ * bf16 tcgen05 GEMMs (forward, dgrad, wgrad) with fp32 accumulation, fp64 batch statistics; the pre-BatchNorm
+ * activations between the layer passes are fp32 [rows, C] in the caller-owned `saved` blob, which the backward reads
+ * (it is what autograd keeps).
+ * precision: 1 = bf16 operands (one MMA per K step; the autocast mode of BASELINE config 4);
+ *            0 = split operands, x = bf16(x) + bf16(x - bf16(x)), three MMAs per K step: fp32-faithful GEMMs, results
+ *                track the reference's fp32 autograd (rtol 2e-3 in the tests).  Forward and backward must use the same value.
+ * Supported: Cout_l a multiple of 16 and <= 512, 3 + D <= 512.
+ *   w[l] [Cout_l, Cin_l] fp32 (the Conv2d weight), bias[l], gamma[l], beta[l] [Cout_l];
+ *   running_mean[l], running_var[l], num_batches_tracked[l]: may be NULL (track_running_stats=False).
+ * forward:  out [B, S, Cout_2] POINT-major (like pcst_sa_mlp_max_f32).
+ * backward: grad_out [B, S, Cout_2]; grads->w[l] [Cout_l, Cin_l], bias[l] (exactly 0: a bias in front of BatchNorm
+ *           has no gradient), gamma[l], beta[l] -- any of them may be NULL to skip it;
+ *           grad_grouped (may be NULL) [B, S, K, 3 + D] = gradient w.r.t. the grouped input
+ *           cat([xyz[idx] - new_xyz, feats[idx]], -1) in the reference's channel order (:99); the caller scatters it
+ *           with pcst_index_points_bwd_f32. */
+typedef struct {
+    const float* w[3];
+    const float* bias[3];
+    const float* gamma[3];
+    const float* beta[3];
+    float* running_mean[3];
+    float* running_var[3];
+    int64_t* num_batches_tracked[3];
+    int cout[3];
+    float eps;      /* nn.BatchNorm2d default 1e-5 */
+    float momentum; /* nn.BatchNorm2d default 0.1 */
+} pcst_mlp3_train_t;
+typedef struct {
+    float* w[3];
+    float* bias[3];
+    float* gamma[3];
+    float* beta[3];
+} pcst_mlp3_grads_t;
+size_t pcst_sa_mlp_train_saved_bytes(int B, int S, int K, int D, const int* cout /*[3]*/);
+size_t pcst_sa_mlp_train_workspace_bytes(int B, int S, int K, int D, const int* cout /*[3]*/, int precision, int backward);
+int pcst_sa_mlp_max_bnstats_bf16(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N,
+                                 int S, int K, int D, const pcst_mlp3_train_t* mlp, int precision, float* out, void* saved,
+                                 size_t saved_bytes, void* ws, size_t ws_bytes, pcst_stream_t stream);
+int pcst_sa_mlp_max_bwd_bf16(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N,
+                             int S, int K, int D, const pcst_mlp3_train_t* mlp, int precision, const void* saved,
+                             size_t saved_bytes, const float* grad_out, const pcst_mlp3_grads_t* grads, float* grad_grouped,
+                             void* ws, size_t ws_bytes, pcst_stream_t stream);
+
 /* ---- nearest-neighbour minimum reduction ------------------------------------------------------
  * a [B,N,3], b [B,M,3] -> rowmin [B,N] = min_j D(a_i, b_j), rowarg [B,N] (optional, may be NULL) =
  * the lowest j attaining it.

@@ -94,6 +94,40 @@ def gen_voxel(HP):
          small_indices=i32(HP(100, 200).downsample(clouds[:, :100])[1]))
 
 
+def gen_train(enc):
+    """TRAIN-mode encoder step (models/pointnet2_encoder.py:74,106-112 with nn.BatchNorm2d batch statistics; the
+    forward / backward of training/trainer.py:78-117 restricted to the encoder): the reference's own forward output,
+    parameter gradients (autograd) and updated BatchNorm buffers for a seeded 2 x 2048-point batch."""
+    torch.manual_seed(42)
+    model = enc.PointNet2Encoder(feature_dim=128)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+                mod.bias.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    sd0 = {k: v.clone().numpy() for k, v in model.state_dict().items()}
+    model.train()
+    x = S.uniform_cloud(21, 2, 2048)
+    coef = torch.randn(2, 128, generator=g)
+    torch.manual_seed(1234)
+    start1 = torch.randint(0, 2048, (2,), dtype=torch.long)
+    start2 = torch.randint(0, 512, (2,), dtype=torch.long)
+    torch.manual_seed(1234)
+    with torch.enable_grad():
+        feat = model(x)
+        (feat * coef).sum().backward()
+    arrays = dict(x=x.numpy(), coef=coef.numpy(), start1=start1.numpy(), start2=start2.numpy(), feature=feat.detach().numpy())
+    for k, v in sd0.items():
+        arrays["sd0." + k] = v
+    for k, v in model.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            arrays["sd1." + k] = v.numpy()
+    for k, prm in model.named_parameters():
+        arrays["grad." + k] = prm.grad.numpy()
+    save("train_encoder", **arrays)
+
+
 def main():
     torch.set_grad_enabled(False)
     os.makedirs(OUT, exist_ok=True)
@@ -101,6 +135,10 @@ def main():
     if "--only-voxel" in sys.argv:
         gen_voxel(HP)
         return
+    if "--only-train" in sys.argv:
+        gen_train(enc)
+        return
+    gen_train(enc)
     gen_voxel(HP)
     M = metrics.PointCloudMetrics("cpu")
 

@@ -30,6 +30,18 @@ class Mlp3(ctypes.Structure):
     _fields_ = [("w", c_void_p * 3), ("scale", c_void_p * 3), ("shift", c_void_p * 3), ("cout", c_int * 3)]
 
 
+class Mlp3Train(ctypes.Structure):
+    """``pcst_mlp3_train_t``."""
+    _fields_ = [("w", c_void_p * 3), ("bias", c_void_p * 3), ("gamma", c_void_p * 3), ("beta", c_void_p * 3),
+                ("running_mean", c_void_p * 3), ("running_var", c_void_p * 3), ("num_batches_tracked", c_void_p * 3),
+                ("cout", c_int * 3), ("eps", c_float), ("momentum", c_float)]
+
+
+class Mlp3Grads(ctypes.Structure):
+    """``pcst_mlp3_grads_t``."""
+    _fields_ = [("w", c_void_p * 3), ("bias", c_void_p * 3), ("gamma", c_void_p * 3), ("beta", c_void_p * 3)]
+
+
 # name -> (restype, argtypes); the single source of truth for the symbol table test
 SIGNATURES = {
     "pcst_version": (c_char_p, []),
@@ -57,6 +69,14 @@ SIGNATURES = {
     "pcst_sa_mlp_max_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int]),
     "pcst_sa_mlp_max_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     POINTER(c_int), c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pcst_sa_mlp_train_saved_bytes": (c_size_t, [c_int, c_int, c_int, c_int, POINTER(c_int)]),
+    "pcst_sa_mlp_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_int]),
+    "pcst_sa_mlp_max_bnstats_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                             POINTER(Mlp3Train), c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
+                                             c_void_p]),
+    "pcst_sa_mlp_max_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         POINTER(Mlp3Train), c_int, c_void_p, c_size_t, c_void_p, POINTER(Mlp3Grads), c_void_p,
+                                         c_void_p, c_size_t, c_void_p]),
     "pcst_nn_min_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_nn_min_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),

@@ -64,12 +64,17 @@ class SetAbstraction(nn.Module):
 
     Inference (``eval()`` and no gradient required) takes the fused path: FPS (+ centroid gather) ->
     ball query -> one fused gather + MLP + max-pool op with conv bias and BatchNorm folded.
-    Training / gradient mode composes the differentiable ``pcst`` gather ops with torch's own
-    Conv2d / BatchNorm2d (batch statistics, running-stat updates and autograd exactly as the
-    reference; those dense layers run on cuBLAS/cuDNN -- library code)."""
+    Training (``train()``) runs the NATIVE train-mode kernels (csrc/sa_mlp_train.cu): tcgen05 GEMMs for forward, dgrad
+    and wgrad, batch-statistic BatchNorm with in-place running-stat updates, ReLU and max-pool gradients -- no cuDNN /
+    cuBLAS.  ``mlp_precision == 1`` feeds bf16 operands (the autocast mode), ``mlp_precision == 0`` split bf16x3
+    operands (fp32-faithful: tracks the reference's fp32 autograd).  The composition of the differentiable ``pcst``
+    gather ops with torch's own Conv2d / BatchNorm2d remains only for eval-mode gradients (frozen BatchNorm), for layer
+    widths outside the kernels' range, and as the explicit ``train_backend = "torch"`` comparison path of the tests."""
 
     #: 0 = fp32 CUDA-core MLP (exact-parity path), 1 = bf16 tcgen05 tensor-core MLP
     mlp_precision: int = 0
+    #: "native" = train mode on the kernels of csrc/sa_mlp_train.cu; "torch" = the Conv2d / BatchNorm2d composition
+    train_backend: str = "native"
 
     def __init__(self, npoint: int, radius: float, nsample: int,
                  in_channel: int, mlp: List[int], group_all: bool = False):
@@ -88,13 +93,14 @@ class SetAbstraction(nn.Module):
         self._fold_key = None
         self._fold = None
         self._packed = {}
+        self._native_steps = 0  # train-mode kernel calls: they update the BatchNorm buffers behind torch's version counters
 
     # -- eval-mode folding of conv bias + BatchNorm into per-channel (scale, shift) ------------------
     def _folded(self):
         tensors = []
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
-        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors) + (self._native_steps,)
         if key != self._fold_key:
             ws, scs, shs = [], [], []
             cin_pad = 0
@@ -140,6 +146,23 @@ class SetAbstraction(nn.Module):
         needs = any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters())
         return not needs
 
+    def _native_train_ok(self, D: int) -> bool:
+        """Train mode on the native tensor-core kernels: three layers of supported widths, ordinary BatchNorm2d
+        (affine, a numeric momentum, one eps), precision 1."""
+        if not self.training or len(self.mlp_convs) != 3 or self.train_backend != "native":
+            return False
+        bns = list(self.mlp_bns)
+        if any((not bn.affine) or bn.momentum is None or bn.eps != bns[0].eps or bn.momentum != bns[0].momentum for bn in bns):
+            return False
+        return ops.sa_mlp_train_supported(D, [conv.out_channels for conv in self.mlp_convs])
+
+    def _mlp_train_native(self, xyz, points, new_xyz, group_idx) -> torch.Tensor:
+        """-> [B,C_out,S] (channel-first view of the kernels' point-major output)."""
+        out = ops.sa_mlp_train(xyz, points, new_xyz, group_idx, list(self.mlp_convs), list(self.mlp_bns),
+                               precision=int(self.mlp_precision))
+        self._native_steps += 1
+        return out.permute(0, 2, 1)
+
     def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor] = None,
                 start: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """``start`` (optional, [B] int64 on the device) overrides the FPS start draw; by default it is
@@ -155,6 +178,8 @@ class SetAbstraction(nn.Module):
                 packed, couts, cluster = self._packed_params(B, 1, N)
                 new_points = ops.sa_mlp_max(xyz, points, None, None, packed, couts, self.mlp_precision, cluster)  # [B,1,C]
                 return new_xyz, new_points[:, 0, :cout]
+            if self._native_train_ok(0 if points is None else points.shape[2]):
+                return new_xyz, self._mlp_train_native(xyz, points, None, None)[:, :, 0]
             if points is not None:
                 grouped_points = torch.cat([xyz.view(B, 1, N, 3), points.view(B, 1, N, -1)], dim=-1)
             else:
@@ -165,6 +190,8 @@ class SetAbstraction(nn.Module):
         new_xyz, group_idx = self._sample_group(xyz, start)
         if fused:
             return new_xyz, self._mlp_fused(xyz, points, new_xyz, group_idx)
+        if self._native_train_ok(0 if points is None else points.shape[2]):
+            return new_xyz, self._mlp_train_native(xyz, points, new_xyz, group_idx)
         new_points = ops.group(xyz, points, new_xyz, group_idx)                # :94-101
         new_points = self.apply_mlp(new_points)
         return new_xyz, new_points

@@ -560,3 +560,137 @@ def voxel_representatives(xyz: Tensor, xyz_min: Tensor, voxel_size: Tensor) -> T
 def _(xyz, xyz_min, voxel_size):
     B, N = xyz.shape[0], xyz.shape[1]
     return xyz.new_empty(B, N, dtype=torch.int64), xyz.new_empty(B, dtype=torch.int32)
+
+
+# ------------------------------------------------------------- SA MLP, training mode (batch-stat BatchNorm + autograd)
+
+
+def sa_mlp_train_supported(D: int, couts: List[int]) -> bool:
+    """Shapes the train-mode tensor-core kernels cover: 3 layers, Cout a multiple of 16 and <= 512, 3 + D <= 512."""
+    return len(couts) == 3 and all(c % 16 == 0 and 0 < c <= 512 for c in couts) and 3 + D <= 512
+
+
+class _SaMlpTrain(torch.autograd.Function):
+    """relu(bn(conv(.))) x 3 + max over each group, nn.BatchNorm2d in TRAINING mode (models/pointnet2_encoder.py:74,
+    106-112), forward and backward on the tcgen05 kernels of csrc/sa_mlp_train.cu.  Running statistics and
+    num_batches_tracked are updated in place by the forward, exactly once per call, like the module would."""
+
+    @staticmethod
+    def forward(ctx, xyz, feats, new_xyz, idx, eps, momentum, precision, bn_buffers, *params):
+        # params = (w0, b0, gamma0, beta0, w1, ..., beta2); bn_buffers = [(running_mean, running_var, num_batches_tracked)] * 3
+        lib = _lib.load()
+        _need_cuda(xyz, feats, new_xyz, idx, *params)
+        xyz = _f32c(xyz.detach())
+        featsc = None if feats is None else _f32c(feats.detach())
+        new_xyzc = None if new_xyz is None else _f32c(new_xyz.detach())
+        idxc = None if idx is None else _i64c(idx)
+        B, N, _ = xyz.shape
+        D = 0 if featsc is None else featsc.shape[2]
+        S, K = (1, N) if idxc is None else (idxc.shape[1], idxc.shape[2])
+        ps = [_f32c(p.detach().reshape(p.shape[0], -1)) if p.dim() > 1 else _f32c(p.detach()) for p in params]
+        m = _lib.Mlp3Train()
+        for l in range(3):
+            w, b, g, be = ps[4 * l: 4 * l + 4]
+            m.w[l], m.bias[l], m.gamma[l], m.beta[l] = w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr()
+            m.cout[l] = w.shape[0]
+            rm, rv, nbt = bn_buffers[l]
+            m.running_mean[l] = 0 if rm is None else rm.data_ptr()
+            m.running_var[l] = 0 if rv is None else rv.data_ptr()
+            m.num_batches_tracked[l] = 0 if nbt is None else nbt.data_ptr()
+        m.eps, m.momentum = float(eps), float(momentum)
+        couts = [int(m.cout[l]) for l in range(3)]
+        c3 = _cout3(couts)
+        dev = xyz.device
+        out = torch.empty(B, S, couts[2], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nsaved = lib.pcst_sa_mlp_train_saved_bytes(B, S, K, D, c3)
+            if nsaved == 0:
+                raise ValueError("sa_mlp_train: unsupported layer widths (Cout must be a multiple of 16, <= 512; 3 + D <= 512)")
+            saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
+            ws = _workspace(lib.pcst_sa_mlp_train_workspace_bytes(B, S, K, D, c3, int(precision), 0), dev)
+            _call("pcst_sa_mlp_max_bnstats_bf16", _p(xyz), _p(featsc), _p(new_xyzc), _p(idxc), B, N, S, K, D, ctypes.byref(m),
+                  int(precision), _p(out), _p(saved), saved.numel(), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(xyz, featsc, new_xyzc, idxc, saved, *ps)
+        ctx.dims = (B, N, S, K, D, couts, float(eps), float(momentum), int(precision))
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.grouped_grad = (feats is not None and feats.requires_grad) or xyz.requires_grad or \
+            (new_xyz is not None and new_xyz.requires_grad)
+        ctx.needs = (ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        xyz, feats, new_xyz, idx, saved, *ps = ctx.saved_tensors
+        B, N, S, K, D, couts, eps, momentum, precision = ctx.dims
+        dev = xyz.device
+        grad_out = _f32c(grad_out)
+        m = _lib.Mlp3Train()
+        gr = _lib.Mlp3Grads()
+        grads = []
+        for l in range(3):
+            w, b, g, be = ps[4 * l: 4 * l + 4]
+            m.w[l], m.bias[l], m.gamma[l], m.beta[l] = w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr()
+            m.cout[l] = w.shape[0]
+            gl = [torch.empty_like(t) for t in (w, b, g, be)]
+            gr.w[l], gr.bias[l], gr.gamma[l], gr.beta[l] = [t.data_ptr() for t in gl]
+            grads += gl
+        m.eps, m.momentum = eps, momentum
+        c3 = _cout3(couts)
+        want_grouped = any(ctx.needs)
+        gg = torch.empty(B, S, K, 3 + D, dtype=torch.float32, device=dev) if want_grouped else None
+        with torch.cuda.device(dev):
+            ws = _workspace(lib.pcst_sa_mlp_train_workspace_bytes(B, S, K, D, c3, precision, 1), dev)
+            _call("pcst_sa_mlp_max_bwd_bf16", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, ctypes.byref(m),
+                  precision, _p(saved), saved.numel(), _p(grad_out), ctypes.byref(gr), _p(gg), _p(ws), ws.numel(), _stream())
+        g_xyz = g_feats = g_new = None
+        if want_grouped:
+            if idx is None:   # group_all: the group is the cloud itself, in order, nothing subtracted
+                if ctx.needs[0]:
+                    g_xyz = gg[:, 0, :, :3].contiguous()
+                if ctx.needs[1]:
+                    g_feats = gg[:, 0, :, 3:].contiguous()
+            else:
+                if ctx.needs[0]:
+                    g_xyz = index_points_bwd(gg[..., :3].contiguous(), idx, N)
+                if ctx.needs[1]:
+                    g_feats = index_points_bwd(gg[..., 3:].contiguous(), idx, N)
+                if ctx.needs[2]:
+                    g_new = -gg[..., :3].sum(dim=2)
+        pg = [g.reshape(s) for g, s in zip(grads, ctx.param_shapes)]
+        return (g_xyz, g_feats, g_new, None, None, None, None, None, *pg)
+
+
+def sa_mlp_train_unpack_saved(saved: Tensor, rows: int, groups: int, couts: List[int]):
+    """Views into the ``saved`` blob of the train-mode forward (layout of train_plan in csrc/sa_mlp_train.cu):
+    -> ([Z_l fp32 [rows, C_l]], [stat_l fp32 [4, C_l] = mean | 1/sqrt(var + eps) | a | b], argmax int32 [groups, C_2];
+    -1 where the pooled value was clipped by the ReLU).  For tests and debugging."""
+    al = lambda v: (v + 255) // 256 * 256
+    off, Z, stat = 0, [], []
+    for c in couts:
+        Z.append(saved[off: off + rows * c * 4].view(torch.float32).reshape(rows, c))
+        off += al(rows * c * 4)
+    for c in couts:
+        stat.append(saved[off: off + 16 * c].view(torch.float32).reshape(4, c))
+        off += al(16 * c)
+    argmax = saved[off: off + groups * couts[2] * 4].view(torch.int32).reshape(groups, couts[2])
+    return Z, stat, argmax
+
+
+KERNELS_PER_CALL["pcst_sa_mlp_max_bnstats_bf16"] = 13   # 3 x (pack, GEMM, column sums, finalize) + pool
+KERNELS_PER_CALL["pcst_sa_mlp_max_bwd_bf16"] = 18       # 3 packs + 3 x (sums, finalize, wgrad, reduce, dgrad)
+
+
+def sa_mlp_train(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], idx: Optional[Tensor],
+                 convs, bns, precision: int = 1) -> Tensor:
+    """Train-mode shared MLP + max-pool of one SetAbstraction stage -> [B,S,Cout] point-major.
+    ``convs`` / ``bns``: the module's three Conv2d(1x1) / BatchNorm2d layers (parameters differentiable, running
+    statistics updated in place).  ``precision``: 1 = bf16 operands, 0 = split (bf16x3, fp32-faithful) operands."""
+    params, buffers = [], []
+    for conv, bn in zip(convs, bns):
+        params += [conv.weight, conv.bias, bn.weight, bn.bias]
+        if bn.track_running_stats:
+            buffers.append((bn.running_mean, bn.running_var, bn.num_batches_tracked))
+        else:
+            buffers.append((None, None, None))
+    return _SaMlpTrain.apply(xyz, feats, new_xyz, idx, bns[0].eps, bns[0].momentum, int(precision), buffers, *params)

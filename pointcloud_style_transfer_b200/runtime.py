@@ -37,7 +37,7 @@ class GraphedEncoder:
         enc = self.encoder
         key = []
         for sa in (enc.sa1, enc.sa2, enc.sa3):
-            key.append(int(sa.mlp_precision))
+            key.append((int(sa.mlp_precision), sa._native_steps))
             for conv, bn in zip(sa.mlp_convs, sa.mlp_bns):
                 for t in (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var):
                     key.append((t.data_ptr(), t._version))
