@@ -254,6 +254,37 @@ int pcst_knn_f32(const float* query, const float* ref, int B, int Q, int R, int 
 int pcst_knn_interpolate_f32(const float* feat, const int64_t* idx, const double* dist, int B, int R,
                              int Q, int k, int C, float* out, pcst_stream_t stream);
 
+/* ---- NoisePredictor.forward: models/diffusion_model.py:38-61 ----------------------------------
+ * The per-point denoiser MLP (3 -> 128 -> 256 -> F, + time / style conditioning, nblocks residual blocks F -> 2F -> F,
+ * F -> 256 -> 128 -> 3) as ONE fused tcgen05 kernel: activations in shared memory / TMEM, the residual stream as the fp32
+ * TMEM accumulator, weights packed once.  Inference (eval mode: Dropout is the identity).
+ * All weights are the nn.Linear tensors, row-major [out, in] fp32; pe = point_encoder.{0,2,4}, blk_w1 / blk_w2 =
+ * layers.{i}.{0,2}, out = output_mlp.{0,2,4}; time_w [F, time_dim], style_w [F, F].
+ * Supported: feature_dim a multiple of 16 in [16, 256], time_dim even, nblocks <= 8.
+ * points [B,N,3], timestep [B] int64, style [B,F] (the style feature AFTER any CFG masking) -> out [B,N,3].
+ * bf16 operands, fp32 accumulation: within rtol 2e-2 of the reference's fp32 module. */
+typedef struct {
+    const float* pe_w[3];
+    const float* pe_b[3];
+    const float* time_w;
+    const float* time_b;
+    const float* style_w;
+    const float* style_b;
+    const float* blk_w1[8];
+    const float* blk_b1[8];
+    const float* blk_w2[8];
+    const float* blk_b2[8];
+    const float* out_w[3];
+    const float* out_b[3];
+    int feature_dim, time_dim, nblocks;
+} pcst_noise_mlp_t;
+size_t pcst_noise_predictor_packed_bytes(int feature_dim, int time_dim, int nblocks);
+size_t pcst_noise_predictor_workspace_bytes(int B, int feature_dim, int nblocks);
+int pcst_noise_predictor_pack_f32(const pcst_noise_mlp_t* mlp, void* packed, size_t packed_bytes, pcst_stream_t stream);
+int pcst_noise_predictor_f32(const float* points, const int64_t* timestep, const float* style, int B, int N, int feature_dim,
+                             int time_dim, int nblocks, const void* packed, float* out, void* ws, size_t ws_bytes,
+                             pcst_stream_t stream);
+
 /* ---- voxel-grid downsample: HierarchicalProcessor._voxel_grid_downsample_torch, models/diffusion_model.py:69-122 --
  * (the step in front of the encoder and the denoiser on every 120k-point scan.)
  * pcst_minmax_f32: out [B,6] = per-cloud (min x, min y, min z, max x, max y, max z), :78-79.

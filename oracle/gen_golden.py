@@ -128,6 +128,27 @@ def gen_train(enc):
     save("train_encoder", **arrays)
 
 
+def gen_noise_predictor():
+    """NoisePredictor.forward (models/diffusion_model.py:38-61), eval mode, on a small configuration (feature_dim 64,
+    time_embed_dim 32: a 0.3 MB fixture; the default 256 / 128 configuration is compared on the GPU against the same
+    formulation, which test_noise_predictor_module_equals_reference_formulation ties to this one)."""
+    import models.diffusion_model as rdm
+    from config.config import Config as RefConfig
+
+    cfg = RefConfig()
+    cfg.feature_dim, cfg.time_embed_dim = 64, 32
+    torch.manual_seed(5)
+    net = rdm.NoisePredictor(cfg).eval()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 333, 3, generator=g)
+    t = torch.tensor([0, 17, 999])
+    style = torch.randn(3, 64, generator=g)
+    style[2] = 0.0                      # the unconditional branch of classifier-free guidance
+    out = net(x, t, style)
+    save("noise_predictor", x=x.numpy(), t=t.numpy(), style=style.numpy(), out=out.numpy(),
+         **{"sd." + k: v.numpy() for k, v in net.state_dict().items()})
+
+
 def main():
     torch.set_grad_enabled(False)
     os.makedirs(OUT, exist_ok=True)
@@ -138,7 +159,11 @@ def main():
     if "--only-train" in sys.argv:
         gen_train(enc)
         return
+    if "--only-noise" in sys.argv:
+        gen_noise_predictor()
+        return
     gen_train(enc)
+    gen_noise_predictor()
     gen_voxel(HP)
     M = metrics.PointCloudMetrics("cpu")
 

@@ -37,6 +37,14 @@ class Mlp3Train(ctypes.Structure):
                 ("cout", c_int * 3), ("eps", c_float), ("momentum", c_float)]
 
 
+class NoiseMlp(ctypes.Structure):
+    """``pcst_noise_mlp_t``."""
+    _fields_ = [("pe_w", c_void_p * 3), ("pe_b", c_void_p * 3), ("time_w", c_void_p), ("time_b", c_void_p),
+                ("style_w", c_void_p), ("style_b", c_void_p), ("blk_w1", c_void_p * 8), ("blk_b1", c_void_p * 8),
+                ("blk_w2", c_void_p * 8), ("blk_b2", c_void_p * 8), ("out_w", c_void_p * 3), ("out_b", c_void_p * 3),
+                ("feature_dim", c_int), ("time_dim", c_int), ("nblocks", c_int)]
+
+
 class Mlp3Grads(ctypes.Structure):
     """``pcst_mlp3_grads_t``."""
     _fields_ = [("w", c_void_p * 3), ("bias", c_void_p * 3), ("gamma", c_void_p * 3), ("beta", c_void_p * 3)]
@@ -76,6 +84,11 @@ SIGNATURES = {
                                              c_void_p]),
     "pcst_sa_mlp_max_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                          POINTER(Mlp3Train), c_int, c_void_p, c_size_t, c_void_p, POINTER(Mlp3Grads), c_void_p,
+                                         c_void_p, c_size_t, c_void_p]),
+    "pcst_noise_predictor_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcst_noise_predictor_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcst_noise_predictor_pack_f32": (c_int, [POINTER(NoiseMlp), c_void_p, c_size_t, c_void_p]),
+    "pcst_noise_predictor_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                          c_void_p, c_size_t, c_void_p]),
     "pcst_nn_min_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_nn_min_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

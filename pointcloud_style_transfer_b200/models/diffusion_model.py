@@ -1,11 +1,15 @@
 """Drop-in for ``HierarchicalProcessor`` of the reference's models/diffusion_model.py: the 3-NN
 inverse-distance upsample (the north-star's "feature-propagation interpolation", §8(a) row a12) and the
 voxel-grid downsample in front of the encoder (first "next" row)."""
-from typing import Tuple
+import math
+from typing import Optional, Tuple
 
 import torch
+import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import ops
+from .pointnet2_encoder import PointNet2Encoder
 
 
 class HierarchicalProcessor:
@@ -117,3 +121,214 @@ class HierarchicalProcessor:
                 result[unknown] = ops.knn_interpolate(vals[None], nbr, dist)[0]
             outs.append(result)
         return torch.stack(outs)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The callers either side of the hot path: the reference's model classes with the same
+# names, constructor arguments, attribute / state_dict names and forward signatures (models/diffusion_model.py:15-61,
+# 156-300), so that its checkpoints load and its trainer / inference scripts run against this package.  The per-point
+# denoiser runs as one fused tcgen05 kernel at inference (ops.noise_predictor); in training its nn.Linear stack stays
+# on torch autograd (library GEMMs: out of the hot-path scope) while the style encoder under it
+# trains on the native kernels.
+# ----------------------------------------------------------------------------------------------------------------------
+class TimeEmbedding(nn.Module):
+    """models/diffusion_model.py:15-26: sinusoidal embedding [sin(t f_j), cos(t f_j)], f_j = 10000^(-j / (dim/2 - 1))."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, t: torch.Tensor) -> torch.Tensor:
+        half = self.dim // 2
+        freq = torch.exp(torch.arange(half, device=t.device) * -(math.log(10000) / (half - 1)))
+        arg = t[:, None] * freq[None, :]
+        return torch.cat((arg.sin(), arg.cos()), dim=-1)
+
+
+class StyleEncoder(nn.Module):
+    """models/diffusion_model.py:28-36: PointNet2Encoder -> Linear-ReLU-Dropout-Linear-ReLU."""
+
+    def __init__(self, feature_dim: int = 256, mlp_precision: int = 0):
+        super().__init__()
+        self.encoder = PointNet2Encoder(input_channels=3, feature_dim=feature_dim, mlp_precision=mlp_precision)
+        self.style_mlp = nn.Sequential(nn.Linear(feature_dim, 512), nn.ReLU(), nn.Dropout(0.1),
+                                       nn.Linear(512, feature_dim), nn.ReLU())
+
+    def forward(self, points: torch.Tensor) -> torch.Tensor:
+        return self.style_mlp(self.encoder(points))
+
+
+class NoisePredictor(nn.Module):
+    """models/diffusion_model.py:38-61.  ``eval()`` without gradients on CUDA runs the fused tensor-core kernel
+    (csrc/noise_mlp_tc.cu, bf16 operands / fp32 accumulate, rtol 2e-2); training runs the nn.Linear stack."""
+
+    #: False forces the nn.Linear formulation at inference too (fp32 comparison path of the tests)
+    fused_inference: bool = True
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        fd = config.feature_dim
+        self.point_encoder = nn.Sequential(nn.Linear(3, 128), nn.ReLU(), nn.Linear(128, 256), nn.ReLU(), nn.Linear(256, fd))
+        self.time_embedding = TimeEmbedding(config.time_embed_dim)
+        self.time_proj = nn.Linear(config.time_embed_dim, fd)
+        self.style_proj = nn.Linear(fd, fd)
+        self.layers = nn.ModuleList([nn.Sequential(nn.Linear(fd, fd * 2), nn.ReLU(), nn.Linear(fd * 2, fd), nn.Dropout(0.1))
+                                     for _ in range(6)])
+        self.output_mlp = nn.Sequential(nn.Linear(fd, 256), nn.ReLU(), nn.Linear(256, 128), nn.ReLU(), nn.Linear(128, 3))
+        self._packed = None
+        self._packed_key = None
+
+    def _packed_params(self) -> torch.Tensor:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if key != self._packed_key:
+            self._packed = ops.noise_predictor_pack(
+                [self.point_encoder[0], self.point_encoder[2], self.point_encoder[4]], self.time_proj, self.style_proj,
+                [(blk[0], blk[2]) for blk in self.layers],
+                [self.output_mlp[0], self.output_mlp[2], self.output_mlp[4]])
+            self._packed_key = key
+        return self._packed
+
+    def _fused_ok(self, *tensors) -> bool:
+        if self.training or not self.fused_inference or not tensors[0].is_cuda:
+            return False
+        if not ops.noise_predictor_supported(self.style_proj.out_features, self.time_proj.in_features, len(self.layers)):
+            return False
+        if not torch.is_grad_enabled():
+            return True
+        return not (any(t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters()))
+
+    def forward(self, noisy_points: torch.Tensor, timestep: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
+        if self._fused_ok(noisy_points, style_feat):
+            return ops.noise_predictor(noisy_points, timestep, style_feat, self._packed_params(),
+                                       self.style_proj.out_features, self.time_proj.in_features, len(self.layers))
+        point_feat = self.point_encoder(noisy_points)                                                   # :54
+        time_feat = self.time_proj(self.time_embedding(timestep)).unsqueeze(1)                          # :55
+        x = point_feat + time_feat + self.style_proj(style_feat).unsqueeze(1)                           # :56-57
+        for layer in self.layers:                                                                       # :58-59
+            x = layer(x) + x
+        return self.output_mlp(x)                                                                       # :60
+
+
+class PointCloudDiffusionModel(nn.Module):
+    """models/diffusion_model.py:156-190."""
+
+    def __init__(self, config, mlp_precision: int = 0):
+        super().__init__()
+        self.config = config
+        self.style_encoder = StyleEncoder(feature_dim=config.feature_dim, mlp_precision=mlp_precision)
+        self.noise_predictor = NoisePredictor(config)
+        self.hierarchical_processor = HierarchicalProcessor(total_points=config.total_points,
+                                                            global_points=config.global_points)
+
+    def forward(self, noisy_points: torch.Tensor, timestep: torch.Tensor, condition_points: torch.Tensor,
+                cond_drop_prob: float = 0.0, use_hierarchical: bool = True):
+        hp, gp = self.hierarchical_processor, self.config.global_points
+        if use_hierarchical and condition_points.shape[1] > gp:                                         # :169-173
+            condition_points, _ = hp.downsample(condition_points)
+        style_feat = self.style_encoder(condition_points)
+        if cond_drop_prob > 0:                                                                          # :175-177
+            keep = torch.rand(style_feat.shape[0], 1, device=style_feat.device) > cond_drop_prob
+            style_feat = style_feat * keep
+        if use_hierarchical and noisy_points.shape[1] > gp:                                             # :179-184
+            noisy_coarse, noise_indices = hp.downsample(noisy_points)
+            return self.noise_predictor(noisy_coarse, timestep, style_feat), noise_indices
+        return self.noise_predictor(noisy_points, timestep, style_feat), None                           # :186-189
+
+
+class DiffusionProcess:
+    """models/diffusion_model.py:193-300: noise schedules, ``q_sample``, and the CFG-guided / plain DDIM sampling loops.
+    The loops keep the reference's arithmetic step for step; the hierarchical pieces they call (voxel downsample, fused
+    denoiser, 3-NN upsample) are this package's kernels, so nothing leaves the device inside a step."""
+
+    def __init__(self, config, device: str = "cuda"):
+        self.num_timesteps = config.num_timesteps
+        self.device = device
+        self.betas = self._get_beta_schedule(config.beta_schedule, config.noise_schedule_offset).to(device)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.alphas_cumprod_prev = F.pad(self.alphas_cumprod[:-1], (1, 0), value=1.0)
+        self.sqrt_alphas_cumprod = torch.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = torch.sqrt(1.0 - self.alphas_cumprod)
+
+    def _get_beta_schedule(self, schedule_name: str, offset: float = 0.0) -> torch.Tensor:
+        T = self.num_timesteps
+        if schedule_name == "cosine":                                                                   # :205-209
+            x = torch.linspace(0, T, T + 1, device=self.device)
+            ac = torch.cos(((x / T) + 0.008 + offset) / 1.008 * torch.pi * 0.5) ** 2
+            ac = ac / ac[0]
+            return torch.clip(1 - (ac[1:] / ac[:-1]), 0.0001, 0.9999)
+        if schedule_name == "linear":                                                                   # :210-211
+            return torch.linspace(0.0001, 0.02, T, device=self.device)
+        raise NotImplementedError(f"unknown beta schedule: {schedule_name}")
+
+    def q_sample(self, x_start: torch.Tensor, t: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """:214-219 -> (noisy points, the noise that was added)."""
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        t = torch.clamp(t, 0, self.num_timesteps - 1)
+        a = self.sqrt_alphas_cumprod[t].view(-1, 1, 1)
+        s = self.sqrt_one_minus_alphas_cumprod[t].view(-1, 1, 1)
+        return a * x_start + s * noise, noise
+
+    def _apply_geometric_constraints(self, points: torch.Tensor, target_range: float = 1.8) -> torch.Tensor:
+        return torch.tanh(points / target_range) * target_range                                         # :221-222
+
+    def _ddim_update(self, x, noise, alpha_t, alpha_prev, source_points=None):
+        """One DDIM step (:253-260 / :289-297): predicted x0, optional pull towards the source, tanh range constraint."""
+        pred_x0 = (x - torch.sqrt(1.0 - alpha_t) * noise) / (torch.sqrt(alpha_t) + 1e-8)
+        if source_points is not None:
+            pred_x0 = pred_x0 + 0.1 * (source_points - pred_x0)
+        pred_x0 = self._apply_geometric_constraints(pred_x0)
+        return torch.sqrt(alpha_prev) * pred_x0 + torch.sqrt(1.0 - alpha_prev) * noise
+
+    @torch.no_grad()
+    def guided_sample_loop(self, model, source_points: torch.Tensor, condition_points: torch.Tensor,
+                           num_inference_steps: int = 50, guidance_scale: float = 7.5) -> torch.Tensor:
+        """:225-261.  Classifier-free-guided DDIM: every step denoises the conditional and the unconditional copy of the
+        current sample on its coarse (voxel-downsampled) points and interpolates the predicted noise back to all points."""
+        device, shape = source_points.device, source_points.shape
+        B = shape[0]
+        hp = model.hierarchical_processor
+        style_feat = model.style_encoder(hp.downsample(condition_points)[0])
+        style_in = torch.cat([style_feat, torch.zeros_like(style_feat)])
+        x = torch.randn(shape, device=device)
+        timesteps_host = torch.linspace(self.num_timesteps - 1, 0, num_inference_steps).long()   # :236, computed on the CPU
+        timesteps = timesteps_host.to(device)
+        timesteps_host = timesteps_host.tolist()
+        ac = self.alphas_cumprod
+        one = torch.ones((), device=device)
+        for i in range(num_inference_steps):
+            t = timesteps[i]
+            x_in = torch.cat([x, x])
+            t_in = t.expand(2 * B).contiguous()
+            x_coarse, x_indices = hp.downsample(x_in)
+            noise_coarse = model.noise_predictor(x_coarse, t_in, style_in)
+            both = hp.upsample_knn(noise_coarse, x_in, x_indices)
+            cond, uncond = both.chunk(2)
+            noise = uncond + guidance_scale * (cond - uncond)
+            # the reference reads the previous timestep from the list while t > 0, else "no previous step" (:251-252)
+            alpha_prev = ac[timesteps[i + 1]] if (i + 1 < num_inference_steps and timesteps_host[i] > 0) else one
+            x = self._ddim_update(x, noise, ac[t], alpha_prev, source_points)
+        return x
+
+    @torch.no_grad()
+    def ddim_sample_loop(self, model, shape, condition_points: torch.Tensor, num_inference_steps: int = 50) -> torch.Tensor:
+        """:263-300 (unguided)."""
+        device = condition_points.device
+        x = torch.randn(shape, device=device)
+        timesteps = torch.linspace(self.num_timesteps - 1, 0, num_inference_steps, dtype=torch.long, device=device)
+        hier = shape[1] > model.config.global_points
+        ac = self.alphas_cumprod
+        one = torch.ones((), device=device)
+        for i in range(num_inference_steps):
+            t = timesteps[i]
+            batch_t = t.expand(shape[0]).contiguous()
+            if hier:
+                noise_coarse, indices = model(x, batch_t, condition_points, cond_drop_prob=0, use_hierarchical=True)
+                noise = model.hierarchical_processor.upsample_knn(noise_coarse, x, indices)
+            else:
+                noise, _ = model(x, batch_t, condition_points, cond_drop_prob=0, use_hierarchical=False)
+            alpha_prev = ac[timesteps[i + 1]] if i + 1 < num_inference_steps else one
+            x = self._ddim_update(x, noise, ac[t], alpha_prev)
+        return x

@@ -694,3 +694,66 @@ def sa_mlp_train(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor]
         else:
             buffers.append((None, None, None))
     return _SaMlpTrain.apply(xyz, feats, new_xyz, idx, bns[0].eps, bns[0].momentum, int(precision), buffers, *params)
+
+
+# ------------------------------------------------------------------------- NoisePredictor (fused per-point MLP chain)
+
+KERNELS_PER_CALL["pcst_noise_predictor_f32"] = 2          # conditioning prep + the fused chain
+KERNELS_PER_CALL["pcst_noise_predictor_pack_f32"] = 40
+
+
+def noise_predictor_supported(feature_dim: int, time_dim: int, nblocks: int) -> bool:
+    return feature_dim % 16 == 0 and 16 <= feature_dim <= 256 and time_dim % 2 == 0 and 4 <= time_dim <= 1024 and 0 <= nblocks <= 8
+
+
+def noise_predictor_pack(pe, time_proj, style_proj, blocks, out) -> Tensor:
+    """Pack a NoisePredictor's nn.Linear parameters once per parameter version -> uint8 blob (bf16 UMMA weight blocks in
+    the kernel's step order, fp32 biases and conditioning projections).  ``pe`` / ``out``: the three Linear layers of
+    point_encoder / output_mlp; ``blocks``: [(Linear(F,2F), Linear(2F,F))]."""
+    lib = _lib.load()
+    m = _lib.NoiseMlp()
+    keep = []
+
+    def ptr(t):
+        t = _f32c(t.detach())
+        keep.append(t)
+        return t.data_ptr()
+
+    for i in range(3):
+        m.pe_w[i], m.pe_b[i] = ptr(pe[i].weight), ptr(pe[i].bias)
+        m.out_w[i], m.out_b[i] = ptr(out[i].weight), ptr(out[i].bias)
+    m.time_w, m.time_b = ptr(time_proj.weight), ptr(time_proj.bias)
+    m.style_w, m.style_b = ptr(style_proj.weight), ptr(style_proj.bias)
+    for i, (l1, l2) in enumerate(blocks):
+        m.blk_w1[i], m.blk_b1[i], m.blk_w2[i], m.blk_b2[i] = ptr(l1.weight), ptr(l1.bias), ptr(l2.weight), ptr(l2.bias)
+    m.feature_dim, m.time_dim, m.nblocks = style_proj.out_features, time_proj.in_features, len(blocks)
+    dev = pe[0].weight.device
+    _need_cuda(pe[0].weight)
+    with torch.cuda.device(dev):
+        nb = lib.pcst_noise_predictor_packed_bytes(m.feature_dim, m.time_dim, m.nblocks)
+        if nb == 0:
+            raise ValueError("noise_predictor_pack: unsupported sizes (feature_dim a multiple of 16 in [16, 256], <= 8 blocks)")
+        packed = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _call("pcst_noise_predictor_pack_f32", ctypes.byref(m), _p(packed), nb, _stream())
+    return packed
+
+
+@torch.library.custom_op("pcst::noise_predictor", mutates_args=(), device_types="cuda")
+def noise_predictor(points: Tensor, timestep: Tensor, style: Tensor, packed: Tensor, feature_dim: int, time_dim: int,
+                    nblocks: int) -> Tensor:
+    """points [B,N,3] fp32, timestep [B] int64, style [B,F] -> predicted noise [B,N,3] (eval-mode NoisePredictor)."""
+    lib = _lib.load()
+    _need_cuda(points, timestep, style, packed)
+    points, style, timestep = _f32c(points), _f32c(style), _i64c(timestep)
+    B, N, _ = points.shape
+    out = torch.empty(B, N, 3, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        ws = _workspace(lib.pcst_noise_predictor_workspace_bytes(B, feature_dim, nblocks), points.device)
+        _call("pcst_noise_predictor_f32", _p(points), _p(timestep), _p(style), B, N, feature_dim, time_dim, nblocks, _p(packed),
+              _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
+@noise_predictor.register_fake
+def _(points, timestep, style, packed, feature_dim, time_dim, nblocks):
+    return points.new_empty(points.shape[0], points.shape[1], 3, dtype=torch.float32)

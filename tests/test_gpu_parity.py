@@ -674,6 +674,69 @@ def test_train_mode_native_kernels_against_torch_autograd(api, dev, shape, preci
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
+# ------------------------------------------------------------------------- NoisePredictor (next row, rank 2)
+
+
+def _noise_cfg(feature_dim, time_dim):
+    from pointcloud_style_transfer_b200.config import Config
+
+    c = Config()
+    c.feature_dim, c.time_embed_dim = feature_dim, time_dim
+    return c
+
+
+def test_noise_predictor_fused_kernel_against_reference_golden(api, dev, golden):
+    """The fused tcgen05 chain (csrc/noise_mlp_tc.cu) against the REFERENCE's NoisePredictor output (oracle/gen_golden.py,
+    CPU fp32), feature_dim 64: bf16 operands, fp32 accumulation and residual stream: rtol 2e-2 / atol 2e-2, and the error
+    is bf16-sized.  The nn.Linear formulation of the same module (fused_inference off) must equal the golden to fp32."""
+    g = golden("noise_predictor")
+    net = api.dm.NoisePredictor(_noise_cfg(64, 32))
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})
+    net = net.to(dev).eval()
+    x, t, style = (torch.from_numpy(g[k]).to(dev) for k in ("x", "t", "style"))
+    from pointcloud_style_transfer_b200 import ops
+    before = ops.launch_count
+    with torch.no_grad():
+        out = net(x, t, style).cpu().numpy()
+    assert ops.launch_count - before >= 2, "the fused kernel did not run"
+    np.testing.assert_allclose(out, g["out"], rtol=2e-2, atol=2e-2)
+    assert _rel_l2(out, g["out"]) < 1e-2
+    net.fused_inference = False
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            plain = net(x, t, style).cpu().numpy()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    np.testing.assert_allclose(plain, g["out"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,N,F,T", [(2, 30000, 256, 128), (3, 1000, 256, 128), (1, 77, 128, 64), (2, 500, 48, 16)])
+def test_noise_predictor_fused_kernel_against_linear_stack(api, dev, B, N, F, T):
+    """Default configuration (feature_dim 256, time_embed_dim 128) at the coarse-cloud size of the sampling loop, rows that
+    do not fill the last tile, and narrower feature widths: fused kernel vs the module's own nn.Linear formulation in
+    fp32 (which is the reference's, see the golden test), rtol 2e-2 / atol 2e-2."""
+    torch.manual_seed(9)
+    net = api.dm.NoisePredictor(_noise_cfg(F, T)).to(dev).eval()
+    g = torch.Generator().manual_seed(10)
+    x = (torch.randn(B, N, 3, generator=g) * 0.8).to(dev)
+    t = torch.randint(0, 1000, (B,), generator=g).to(dev)
+    style = torch.randn(B, F, generator=g).to(dev)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fused = net(x, t, style).cpu().numpy()
+            net.fused_inference = False
+            ref = net(x, t, style).cpu().numpy()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert fused.shape == (B, N, 3)
+    np.testing.assert_allclose(fused, ref, rtol=2e-2, atol=2e-2)
+    assert _rel_l2(fused, ref) < 1e-2
+
+
 # ------------------------------------------------------------------------------- Chamfer / NN-min
 
 

@@ -48,3 +48,29 @@ def test_patch_reference_swaps_symbols_and_keeps_state_dict_keys():
                          timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().endswith("ok")
+
+
+def test_model_classes_match_reference_goldens_on_cpu(golden):
+    """The caller-side model classes mirror the reference (same state_dict keys, same arithmetic in the nn.Linear
+    formulation): NoisePredictor against the reference's golden output bit for bit, on the CPU."""
+    import numpy as np
+    import torch
+
+    from pointcloud_style_transfer_b200.config import Config
+    from pointcloud_style_transfer_b200.models import diffusion_model as dm
+
+    g = golden("noise_predictor")
+    cfg = Config()
+    cfg.feature_dim, cfg.time_embed_dim = 64, 32
+    net = dm.NoisePredictor(cfg)
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})  # strict: same keys
+    net.eval()
+    with torch.no_grad():
+        out = net(torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), torch.from_numpy(g["style"])).numpy()
+    assert np.array_equal(out, g["out"])
+    model = dm.PointCloudDiffusionModel(Config())
+    assert sum(p.numel() for p in model.parameters()) == 2549827   # SURVEY.md 8(d): the reference's parameter count
+    dp = dm.DiffusionProcess(Config(), "cpu")
+    x0 = torch.randn(2, 10, 3)
+    xt, eps = dp.q_sample(x0, torch.tensor([0, 999]))
+    assert torch.allclose(xt, dp.sqrt_alphas_cumprod[[0, 999]].view(2, 1, 1) * x0 + dp.sqrt_one_minus_alphas_cumprod[[0, 999]].view(2, 1, 1) * eps)
