@@ -81,8 +81,60 @@ class HierarchicalProcessor:
         return torch.stack(downsampled_list), torch.stack(indices_list)
 
     def downsample(self, points: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """models/diffusion_model.py:124-125."""
+        """models/diffusion_model.py:124-125.  ``rng_device == "cuda"`` takes the device-resident variant."""
+        if self.rng_device == "cuda" and points.is_cuda and points.shape[1] > self.global_points:
+            return self.downsample_device(points)
         return self._voxel_grid_downsample_torch(points, self.global_points)
+
+    def downsample_device(self, points: torch.Tensor, generator: Optional[torch.Generator] = None):
+        """The same voxel-grid downsample (:69-122) with NOTHING leaving the device: no host synchronisation, fixed
+        output shapes, capturable in a CUDA graph.  Bounding box and representatives come from
+        the same kernels; ``voxel_size`` is formed by the reference's own tensor expression (:80-85) evaluated on the
+        device, as the reference does when it runs on CUDA; the random thinning / top-up (:95-112) is one draw of uniform
+        keys per point and a top-k: with at least ``target`` occupied voxels a uniformly random subset of the
+        representatives (in random order), otherwise all representatives in ``torch.unique`` order followed by a
+        uniformly random subset of the remaining points -- the reference's selection rule, with the device generator's
+        stream instead of ``torch.randperm``'s."""
+        target = self.global_points
+        B, N, _ = points.shape
+        device = points.device
+        pts = points.detach().float().contiguous()
+        box = ops.minmax(pts)                                                   # [B,6]
+        xyz_range = box[:, 3:] - box[:, :3]                                     # :80
+        xyz_range = torch.where(xyz_range < 1e-6, torch.ones_like(xyz_range), xyz_range)       # :81
+        voxel_size = (xyz_range.prod(dim=1) / target) ** (1 / 3) * 1.2          # :83
+        voxel_size = torch.where(voxel_size < 1e-6, torch.full_like(voxel_size, 1e-3), voxel_size)   # :84-85
+        rep, count = ops.voxel_representatives(pts, box[:, :3].contiguous(), voxel_size)
+        # Candidates: the N slots of the representative list (slot j valid while j < count; the list may name a point twice,
+        # two voxels can share a truncated mean index, and the reference keeps both) followed by the N points themselves
+        # as the top-up pool (points that are representatives excluded, :102-104).
+        ar = torch.arange(N, device=device)
+        valid = ar[None, :] < count[:, None]
+        is_rep = torch.zeros(B, N, dtype=torch.bool, device=device)
+        is_rep.scatter_(1, torch.where(valid, rep, rep[:, :1].expand(B, N)), torch.ones_like(valid))   # count >= 1 always
+        key = torch.rand(B, 2 * N, device=device, generator=generator)
+        enough = (count >= target)[:, None]
+        never = torch.full((), 3.0, device=device)
+        slot_score = torch.where(valid, torch.where(enough, key[:, :N], (ar[None, :] - N).float().expand(B, N)), never)
+        pool_score = torch.where(enough | is_rep, never, key[:, N:])
+        pick = torch.topk(torch.cat([slot_score, pool_score], 1), target, dim=1, largest=False, sorted=True).indices
+        final_indices = torch.gather(torch.cat([rep, ar[None, :].expand(B, N)], 1), 1, pick)
+        return torch.gather(points, 1, final_indices[..., None].expand(-1, -1, 3)), final_indices
+
+    def upsample_knn_device(self, coarse_points: torch.Tensor, original_points: torch.Tensor,
+                            coarse_indices: torch.Tensor) -> torch.Tensor:
+        """``upsample_knn`` (:127-153) for the case the sampling loop produces -- ``coarse_indices`` unique and in range
+        (the output of ``downsample``) -- without host synchronisation or data-dependent shapes: every point of the cloud
+        queries its 3 nearest KNOWN points (a known point finds itself at distance 0) and the known points' own values
+        are written over the interpolated ones, which is what the reference's ``result[idx] = coarse`` does."""
+        C = coarse_points.shape[2]
+        original = original_points.detach().float().contiguous()
+        coarse = coarse_points.detach().float().contiguous()
+        fit = torch.gather(original, 1, coarse_indices[..., None].expand(-1, -1, 3))
+        k = min(3, fit.shape[1])
+        dist, nbr = ops.knn(original, fit, k)
+        out = ops.knn_interpolate(coarse, nbr, dist)
+        return out.scatter(1, coarse_indices[..., None].expand(-1, -1, C), coarse)
 
     def upsample_knn(self, coarse_points: torch.Tensor, original_points: torch.Tensor,
                      coarse_indices: torch.Tensor) -> torch.Tensor:
@@ -310,6 +362,74 @@ class DiffusionProcess:
             # the reference reads the previous timestep from the list while t > 0, else "no previous step" (:251-252)
             alpha_prev = ac[timesteps[i + 1]] if (i + 1 < num_inference_steps and timesteps_host[i] > 0) else one
             x = self._ddim_update(x, noise, ac[t], alpha_prev, source_points)
+        return x
+
+    @torch.no_grad()
+    def guided_sample_loop_device(self, model, source_points: torch.Tensor, condition_points: torch.Tensor,
+                                  num_inference_steps: int = 50, guidance_scale: float = 7.5,
+                                  graph: bool = True, x_init: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The same CFG-guided DDIM loop (:225-261) with every step device-resident: voxel
+        downsample, fused denoiser, 3-NN upsample and the DDIM update run without a host round trip
+        (``downsample_device`` / ``upsample_knn_device``), so ONE step is captured into a CUDA graph and replayed
+        ``num_inference_steps`` times (``graph=True``); the step index, timestep and the two alpha-bar values are read from
+        device tables by an in-graph counter.  ``graph=False`` runs the identical step eagerly (the tests compare the two).
+        The random thinning of the downsample draws from the CUDA default generator in both modes.  Requires the
+        hierarchical path (more points than ``config.global_points``)."""
+        device, shape = source_points.device, source_points.shape
+        B, N, _ = shape
+        hp = model.hierarchical_processor
+        if not (source_points.is_cuda and N > hp.global_points):
+            raise RuntimeError("guided_sample_loop_device: CUDA tensors with more points than config.global_points expected")
+        cond = condition_points
+        if cond.shape[1] > hp.global_points:
+            cond = hp.downsample_device(cond)[0]
+        style_feat = model.style_encoder(cond)
+        style_in = torch.cat([style_feat, torch.zeros_like(style_feat)]).contiguous()
+        ts = torch.linspace(self.num_timesteps - 1, 0, num_inference_steps).long()               # :236 (CPU)
+        prev = [int(ts[i + 1]) if (i + 1 < num_inference_steps and int(ts[i]) > 0) else -1 for i in range(num_inference_steps)]
+        ac = self.alphas_cumprod
+        tab_t = ts.to(device)
+        tab_at = ac[tab_t].contiguous()
+        tab_ap = torch.stack([ac[p] if p >= 0 else torch.ones((), device=device) for p in prev]).contiguous()
+        x0 = torch.randn(shape, device=device) if x_init is None else x_init.to(device).float()
+        x = x0.clone()
+        counter = torch.zeros(1, dtype=torch.long, device=device)
+        source = source_points.float().contiguous()
+
+        def step():
+            t = tab_t.index_select(0, counter)                      # [1]
+            at = tab_at.index_select(0, counter).view(())
+            ap = tab_ap.index_select(0, counter).view(())
+            x_in = torch.cat([x, x])
+            x_coarse, x_indices = hp.downsample_device(x_in)
+            noise_coarse = model.noise_predictor(x_coarse, t.expand(2 * B).contiguous(), style_in)
+            both = hp.upsample_knn_device(noise_coarse, x_in, x_indices)
+            nc, nu = both.chunk(2)
+            noise = nu + guidance_scale * (nc - nu)
+            x.copy_(self._ddim_update(x, noise, at, ap, source))
+            counter.add_(1)
+
+        if not graph:
+            for _ in range(num_inference_steps):
+                step()
+            return x
+        rng = torch.cuda.get_rng_state(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            step()                                                  # warm-up: library load, packing, allocator
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        counter.zero_()
+        x.copy_(x0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        counter.zero_()
+        x.copy_(x0)
+        torch.cuda.set_rng_state(rng, device)                       # the replays start from the caller's generator state
+        for _ in range(num_inference_steps):
+            g.replay()
         return x
 
     @torch.no_grad()
