@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--mlp-precision", type=int, default=int(os.environ.get("PCST_MLP_PRECISION", "1")),
                     help="1 = bf16 tcgen05 shared MLP (north_star's design, default); 0 = fp32 CUDA-core MLP")
     ap.add_argument("--chamfer-steps", type=int, default=5)
+    ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the config-4 training step (0 = skip)")
+    ap.add_argument("--sampling-steps", type=int, default=10, help="DDIM steps timed for the sampling-loop line (0 = skip)")
     ap.add_argument("--batched-scans", type=int, default=-1,
                     help="scans per GPU of the secondary batched-throughput line (0 = skip, -1 = as many as FPS clusters fit at once)")
     args = ap.parse_args()
@@ -417,6 +419,77 @@ def main():
             ms_knn = timed(lambda: D.knn_query_sharded(p_loc, t_loc, 3), max(1, args.chamfer_steps))
         knn_sharded = statistics.mean(ms_knn)
 
+    # ---- BASELINE config 4: full diffusion training step, bf16, 4 scans x 16 384 points per GPU (32 x 16 384 on 8 GPUs):
+    # style encoder forward + backward on the native train-mode kernels, denoiser on torch autocast, Chamfer branch on
+    # (global_points lowered to 4096 as SURVEY.md 8(d) prescribes), one NCCL all-reduce of the flat gradient, AdamW.
+    train_c4 = None
+    if args.train_steps > 0:
+        from pointcloud_style_transfer_b200.config import Config
+        from pointcloud_style_transfer_b200.train_step import DiffusionTrainStep
+        cfg = Config()
+        cfg.total_points, cfg.global_points = 16384, 4096
+        BL = 4
+        torch.manual_seed(7)
+        trainer = DiffusionTrainStep(cfg, dev, mlp_precision=1, world=world)
+        sim = torch.cat([S.lidar_scan((rank * BL + i) % 16, 16384) for i in range(BL)], 0).to(dev)
+        real = torch.cat([S.lidar_scan((rank * BL + i) % 16 + 100, 16384) for i in range(BL)], 0).to(dev)
+        torch.manual_seed(11 + rank)
+        torch.cuda.manual_seed(11 + rank)
+        for _ in range(3):
+            trainer.step(sim, real)
+        l0 = ops.launch_count
+        ms_tr = timed(lambda: trainer.step(sim, real), args.train_steps)
+        train_c4 = (statistics.mean(ms_tr), (ops.launch_count - l0) / (args.train_steps + 1), BL)
+        # where the step's time goes (eager CUDA events around the C-ABI calls of one more step)
+        ops.start_event_log()
+        trainer.step(sim, real)
+        tr_ops = {k: sum(v) for k, v in ops.stop_event_log().items()}
+        del trainer
+
+    # ---- denoiser (NoisePredictor) on the coarse clouds of one CFG step: 2 x 30 000 points ----
+    denoiser = sampling = None
+    if args.sampling_steps > 0:
+        from pointcloud_style_transfer_b200.config import Config
+        from pointcloud_style_transfer_b200.models import diffusion_model as DM
+        cfg = Config()
+        torch.manual_seed(3)
+        model = DM.PointCloudDiffusionModel(cfg, mlp_precision=1).to(dev).eval()
+        proc = DM.DiffusionProcess(cfg, device=str(dev))
+        xc = torch.randn(2, 30000, 3, device=dev)
+        tt = torch.tensor([500, 500], device=dev)
+        st = torch.randn(2, 256, device=dev)
+        net = model.noise_predictor
+        den = {}
+        with torch.no_grad():
+            for name in ("fused_tcgen05_bf16", "torch_linear_fp32", "torch_linear_bf16_autocast"):
+                net.fused_inference = name == "fused_tcgen05_bf16"
+                ctx = torch.autocast("cuda", dtype=torch.bfloat16, enabled=name.endswith("autocast"))
+                with ctx:
+                    for _ in range(3):
+                        net(xc, tt, st)
+                    den[name] = statistics.mean(timed(lambda: net(xc, tt, st), 10))
+            net.fused_inference = True
+        denoiser = den
+        # ---- one CFG-guided DDIM step on a 120k scan: graph-replayed device-resident step vs the host-driven loop ----
+        src, cnd = x_dev, y_dev
+        K_s = args.sampling_steps
+        with torch.no_grad():
+            tg, te = {}, {}
+            torch.cuda.manual_seed(5)
+            proc.guided_sample_loop_device(model, src, cnd, num_inference_steps=2, graph=True)   # warm-up
+            proc.guided_sample_loop_device(model, src, cnd, num_inference_steps=K_s, graph=True, timing=tg)
+            proc.guided_sample_loop_device(model, src, cnd, num_inference_steps=K_s, graph=False, timing=te)
+            torch.manual_seed(5)
+            proc.guided_sample_loop(model, src, cnd, num_inference_steps=1)                        # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            proc.guided_sample_loop(model, src, cnd, num_inference_steps=3)
+            torch.cuda.synchronize()
+            host_ms = (time.perf_counter() - t0) * 1e3 / 3
+        sampling = {"steps": K_s, "graph_replay_ms_per_step": tg["ms_per_step"], "device_eager_ms_per_step": te["ms_per_step"],
+                    "host_loop_ms_per_step": host_ms}
+        del model
+
     def allmax(v):
         if world == 1:
             return v
@@ -445,6 +518,7 @@ def main():
     t_b = allmax(batched) if batched is not None else None
     t_sh = allmax(ch_sharded[0]) if ch_sharded is not None else None
     t_knn = allmax(knn_sharded) if knn_sharded is not None else None
+    t_train = allmax(train_c4[0]) if train_c4 is not None else None
 
     if rank == 0:
         value = world * N_POINTS / (t_dev * 1e-3)
@@ -532,6 +606,33 @@ def main():
             "ranks": {"ms_per_step": rank_ms, "median_step_ms": rank_median, "slowest_single_step_ms": rank_worst, "sm_mhz": rank_mhz,
                       "throttle_reasons_seen": rank_throttled},
         }
+        if t_train is not None:
+            BLc = train_c4[2]
+            line["train_c4"] = {
+                "metric": "training points/sec, full diffusion training step (BASELINE config 4), bf16, %d x 16384 points per GPU "
+                          "(%d x 16384 on %d GPU%s)" % (BLc, BLc * world, world, "" if world == 1 else "s"),
+                "value": world * BLc * 16384 / (t_train * 1e-3), "unit": "points/s", "ms_per_step": t_train, "scaling": "weak",
+                "global_batch": BLc * world, "points_per_scan": 16384, "global_points": 4096,
+                "kernel_launches_per_step": train_c4[1], "op_ms_eager": tr_ops,
+                "what": "q_sample -> voxel downsample (device) -> style encoder fwd (native train-mode tcgen05 kernels, batch-stat "
+                        "BatchNorm) -> denoiser (torch autocast bf16) -> L1 + 0.1 * Chamfer (native) -> backward (native dgrad / "
+                        "wgrad / BatchNorm / Chamfer backward) -> one NCCL all-reduce of the flat gradient (10.2 MB) -> clip -> "
+                        "fused AdamW -> EMA; the loss dict's .item() calls of the reference are inside the step",
+                "dtype": "bf16 GEMM operands (encoder: tcgen05 train kernels; denoiser: autocast), fp32 distances / statistics"}
+        if denoiser is not None:
+            rows_d = 2 * 30000
+            fl = 2.0 * rows_d * (3 * 128 + 128 * 256 + 256 * 256 + 6 * (256 * 512 * 2) + 256 * 256 + 256 * 128 + 128 * 3)
+            bf16_peak2, _ = bf16_peak_tflops()
+            line["denoiser"] = {"metric": "NoisePredictor forward, 2 x 30000 coarse points (one CFG step), ms",
+                                "ms": denoiser, "gflop": fl / 1e9,
+                                "roofline": {"kernel": "noise_mlp_kernel", "bound": "tensor", "unit": "TFLOP/s",
+                                             "achieved": fl / (denoiser["fused_tcgen05_bf16"] * 1e-3) / 1e12, "peak": bf16_peak2,
+                                             "frac": fl / (denoiser["fused_tcgen05_bf16"] * 1e-3) / 1e12 / bf16_peak2}}
+        if sampling is not None:
+            line["sampling_loop"] = dict(sampling, metric="one CFG-guided DDIM step on a 120k-point scan (downsample x2 -> denoiser -> "
+                                         "3-NN upsample x2 -> update), ms per step",
+                                         note="graph = guided_sample_loop_device (one CUDA graph replay per step); host = "
+                                              "guided_sample_loop (the reference's loop structure with host-side RNG draws)")
         if t_b is not None:
             line["batched"] = {"metric": "SA points/sec, %d x 120k-pt scans per GPU in one graph (= concurrent 16-CTA FPS clusters)" % args.batched_scans,
                                "value": world * args.batched_scans * N_POINTS / (t_b * 1e-3), "unit": "points/s",

@@ -367,14 +367,16 @@ class DiffusionProcess:
     @torch.no_grad()
     def guided_sample_loop_device(self, model, source_points: torch.Tensor, condition_points: torch.Tensor,
                                   num_inference_steps: int = 50, guidance_scale: float = 7.5,
-                                  graph: bool = True, x_init: Optional[torch.Tensor] = None) -> torch.Tensor:
+                                  graph: bool = True, x_init: Optional[torch.Tensor] = None,
+                                  timing: Optional[dict] = None) -> torch.Tensor:
         """The same CFG-guided DDIM loop (:225-261) with every step device-resident: voxel
         downsample, fused denoiser, 3-NN upsample and the DDIM update run without a host round trip
         (``downsample_device`` / ``upsample_knn_device``), so ONE step is captured into a CUDA graph and replayed
         ``num_inference_steps`` times (``graph=True``); the step index, timestep and the two alpha-bar values are read from
         device tables by an in-graph counter.  ``graph=False`` runs the identical step eagerly (the tests compare the two).
         The random thinning of the downsample draws from the CUDA default generator in both modes.  Requires the
-        hierarchical path (more points than ``config.global_points``)."""
+        hierarchical path (more points than ``config.global_points``).  ``timing`` (optional dict) receives
+        ``ms_per_step``: CUDA-event time of the step loop alone (no style encoder, warm-up or capture)."""
         device, shape = source_points.device, source_points.shape
         B, N, _ = shape
         hp = model.hierarchical_processor
@@ -409,10 +411,21 @@ class DiffusionProcess:
             x.copy_(self._ddim_update(x, noise, at, ap, source))
             counter.add_(1)
 
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if timing is not None else None
+
+        def finish():
+            if ev is not None:
+                ev[1].record()
+                ev[1].synchronize()
+                timing["ms_per_step"] = ev[0].elapsed_time(ev[1]) / num_inference_steps
+            return x
+
         if not graph:
+            if ev is not None:
+                ev[0].record()
             for _ in range(num_inference_steps):
                 step()
-            return x
+            return finish()
         rng = torch.cuda.get_rng_state(device)
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
@@ -428,9 +441,11 @@ class DiffusionProcess:
         counter.zero_()
         x.copy_(x0)
         torch.cuda.set_rng_state(rng, device)                       # the replays start from the caller's generator state
+        if ev is not None:
+            ev[0].record()
         for _ in range(num_inference_steps):
             g.replay()
-        return x
+        return finish()
 
     @torch.no_grad()
     def ddim_sample_loop(self, model, shape, condition_points: torch.Tensor, num_inference_steps: int = 50) -> torch.Tensor:
