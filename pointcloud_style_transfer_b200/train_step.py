@@ -23,6 +23,25 @@ from .models.diffusion_model import DiffusionProcess, PointCloudDiffusionModel
 from .models.losses import DiffusionLoss
 
 
+def attach_flat_grad(params) -> torch.Tensor:
+    """Make every parameter's ``.grad`` a view into ONE flat fp32 buffer (returned), so that the cross-rank gradient average
+    is a single collective over 4 * numel bytes instead of one per tensor."""
+    params = list(params)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p in params:
+        p.grad = flat[off: off + p.numel()].view_as(p)
+        off += p.numel()
+    return flat
+
+
+def average_gradients(flat_grad: torch.Tensor, world: int) -> None:
+    """DDP-style gradient averaging: all-reduce(SUM) of the flat buffer, then divide by the number of ranks."""
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        flat_grad.div_(world)
+
+
 class DiffusionTrainStep:
     def __init__(self, config, device, mlp_precision: int = 1, world: int = 1, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  quiet: bool = True):
@@ -41,12 +60,7 @@ class DiffusionTrainStep:
         else:
             self.loss_fn = DiffusionLoss(noise_weight=1.0, chamfer_weight=config.lambda_chamfer)
         params = [p for p in self.model.parameters() if p.requires_grad]
-        # flat gradient buffer: every .grad is a view, so the cross-rank average is one collective
-        self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.device)
-        off = 0
-        for p in params:
-            p.grad = self.flat_grad[off: off + p.numel()].view_as(p)
-            off += p.numel()
+        self.flat_grad = attach_flat_grad(params)   # every .grad is a view: the cross-rank average is one collective
         self.params = params
         self.optimizer = torch.optim.AdamW(params, lr=config.learning_rate, weight_decay=config.weight_decay, betas=(0.9, 0.95),
                                            fused=True)
@@ -85,9 +99,7 @@ class DiffusionTrainStep:
         gradient_accumulation_steps = 1)."""
         loss, loss_dict = self.loss(sim_points, real_points, t, noise)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
-            self.flat_grad.div_(self.world)
+        average_gradients(self.flat_grad, self.world)
         torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=False)

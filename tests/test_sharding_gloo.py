@@ -67,8 +67,16 @@ def _worker(rank, world, port, q):
         feats = D.encode_scans_sharded(_ToyEncoder(), scans)
         # 3-NN with the queries sharded and the (ragged) reference shards all-gathered: results stay sharded
         kd, ki = D.knn_query_sharded(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), 3, knn_fn=_oracle_knn)
+        # DDP-style gradient averaging of the config-4 training step: every .grad a view into one flat buffer, one all-reduce
+        from pointcloud_style_transfer_b200.train_step import attach_flat_grad, average_gradients
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(3, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        flat = attach_flat_grad(net.parameters())
+        net(scans[rank]).square().sum().backward()          # rank-dependent batch
+        views_ok = all(p.grad.data_ptr() >= flat.data_ptr() for p in net.parameters())
+        average_gradients(flat, world)
         q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy(), cd1.numpy(), cdm1.numpy(), cde.numpy(),
-               (lo, hi), kd.numpy(), ki.numpy()))
+               (lo, hi), kd.numpy(), ki.numpy(), views_ok, flat.numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -91,7 +99,16 @@ def test_query_sharded_chamfer_and_scan_sharding_world2(oracle):
     ref_feats = _ToyEncoder()(scans).numpy()
     ref_e = oracle.chamfer_distance_chunked_optimized(pred.numpy()[:, :5], target.numpy())
     ref_kd, ref_ki = oracle.knn(pred.numpy(), target.numpy(), 3)
-    for rank, ok_gather, cd, cdm, feats, cd1, cdm1, cde, (lo, hi), kd, ki in res:
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(3, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    want = 0
+    for r in range(2):
+        net.zero_grad()
+        net(scans[r]).square().sum().backward()
+        want = want + torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy() / 2
+    for rank, ok_gather, cd, cdm, feats, cd1, cdm1, cde, (lo, hi), kd, ki, views_ok, flat in res:
+        assert views_ok
+        np.testing.assert_allclose(flat, want, rtol=1e-6, atol=1e-7)   # both ranks hold the average of the two gradients
         np.testing.assert_array_equal(ki, ref_ki[:, lo:hi])   # indices refer to the gathered (rank-ordered) references
         np.testing.assert_array_equal(kd, ref_kd[:, lo:hi])
         assert ok_gather
