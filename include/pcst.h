@@ -243,8 +243,14 @@ int pcst_chamfer_bwd_f32(const float* pred, const float* target, const int64_t* 
  * call sites models/diffusion_model.py:146-147, evaluation/metrics.py:126-127,152-153.
  * query [B,Q,3], ref [B,R,3] fp32 -> idx [B,Q,k] int64, dist [B,Q,k] fp64 ascending (Euclidean);
  * distances are evaluated in fp64 as sqrt(((dx*dx)+(dy*dy))+(dz*dz)), ties to the lower index.
- * 1 <= k <= 16, k <= R. */
+ * 1 <= k <= 16, k <= R.  Large self queries (query == ref, >= 16384 points) are searched through a three-level uniform grid
+ * over the references (counting sort by cell, ring walk with an exact stopping bound: the reference's own search is a
+ * kd-tree); results are identical to the sweep's. */
 size_t pcst_knn_workspace_bytes(int B, int Q, int R, int k);
+/* How many kernels pcst_knn_f32 launches for this shape (1-2: brute-force sweep (+ merge); 10: exact multi-level grid search
+ * over the reference cloud, the default for large self queries (query == ref) -- same results bit for bit).  For launch
+ * accounting. */
+int pcst_knn_kernel_launches(int B, int Q, int R, int k, int self_query);
 int pcst_knn_f32(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx,
                  double* dist, void* ws, size_t ws_bytes, pcst_stream_t stream);
 

@@ -102,6 +102,7 @@ SIGNATURES = {
     "pcst_chamfer_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                      c_void_p, c_void_p]),
     "pcst_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pcst_knn_kernel_launches": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "pcst_knn_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                              c_void_p]),
     "pcst_knn_interpolate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,

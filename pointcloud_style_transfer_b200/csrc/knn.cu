@@ -27,7 +27,8 @@ template <int KMAX>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q, int R, int k,
            int64_t* __restrict__ idx, double* __restrict__ dist, int splits, int tiles_per_split,
-           double* __restrict__ part_d, int* __restrict__ part_i) {
+           double* __restrict__ part_d, int* __restrict__ part_i, const int* __restrict__ qlist = nullptr,
+           const int* __restrict__ qcount = nullptr) {
     // reference points of the tile as pairs of consecutive candidates per component, so that one packed
     // FADD2 / FMUL2 / FFMA2 sequence prefilters two candidates against the thread's query
     // (KMAX <= 4) or as float4 rows, one broadcast LDS.128 per candidate (longer lists)
@@ -36,8 +37,15 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q
     float2* ty = tx + kKnnTile / 2;
     float2* tz = ty + kKnnTile / 2;
     const int b = blockIdx.y;
-    const int q = blockIdx.x * kKnnThreads + threadIdx.x;
-    const bool active = q < Q;
+    int q = blockIdx.x * kKnnThreads + threadIdx.x;
+    bool active = q < Q;
+    if (qlist) {
+        // the queries the grid search handed back (knn_grid.cu): slot -> query index; CTAs past the list leave at once
+        const int n = qcount[b];
+        if ((int)blockIdx.x * kKnnThreads >= n) return;
+        active = q < n;
+        q = active ? qlist[(size_t)b * Q + q] : 0;
+    }
     const float* qp = query + ((size_t)b * Q + (active ? q : 0)) * 3;
     const float fx = qp[0], fy = qp[1], fz = qp[2];
     const double qx = fx, qy = fy, qz = fz;
@@ -203,6 +211,36 @@ __global__ void knn_interpolate_kernel(const float* __restrict__ feat, const int
     }
 }
 
+size_t knn_grid_workspace_bytes(int B, int Q, int R);
+int knn_grid_run(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist, void* ws,
+                 cudaStream_t stream);
+
+// brute-force sweep restricted to the queries listed in qlist [B, Q] (first qcount[b] entries of row b): the grid search's
+// fallback for queries it could not finish inside its ring budget
+int knn_sweep_listed(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist,
+                     const int* qlist, const int* qcount, cudaStream_t stream) {
+    const int tiles = (R + kKnnTile - 1) / kKnnTile;
+    dim3 grid((Q + kKnnThreads - 1) / kKnnThreads, B, 1);
+    if (k <= 1) knn_kernel<1><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
+    else if (k <= 4) knn_kernel<4><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
+    else if (k <= 9) knn_kernel<9><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
+    else knn_kernel<16><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
+    return check_cuda(cudaGetLastError(), "knn_kernel (listed queries)");
+}
+
+// The exact grid search (knn_grid.cu) is the default for large SELF queries (uniformity_score's 9-NN of a cloud against
+// itself, evaluation/metrics.py:152-153: every query sits on a reference, so the ring walk ends at once; measured 2.8 ms
+// against 9.6 ms for the sweep at 120k points).  Between two different clouds its gain depends on how evenly the references
+// fill their box: 1.00 against 1.35 ms for the 90k x 30k interpolation of a LiDAR scan, no gain between two different
+// scans, and a loss on the Gaussian noise clouds of the early sampling steps (a uniform cell edge cannot serve a 200:1
+// density contrast; profiles/r02/knn_grid.md), so the sweep stays the default there.  knn.grid = 1 / 2 forces it on / off.
+static bool knn_use_grid(int Q, int R, bool self_query = false) {
+    const int t = tuning("knn.grid", 0);
+    if (t == 1) return true;
+    if (t == 2) return false;
+    return self_query && R >= 16384;
+}
+
 }  // namespace pcst
 
 using namespace pcst;
@@ -219,9 +257,17 @@ static int knn_splits(int B, int Q, int R) {
 
 extern "C" size_t pcst_knn_workspace_bytes(int B, int Q, int R, int k) {
     if (B <= 0 || Q <= 0 || R <= 0 || k <= 0) return 0;
+    // (a caller cannot say here whether query == ref: size for the grid whenever a self query of this shape would take it)
+    if (knn_use_grid(Q, R, Q == R)) return knn_grid_workspace_bytes(B, Q, R);
     const int s = knn_splits(B, Q, R);
     if (s == 1) return 0;
     return align_up((size_t)B * Q * s * k * sizeof(double), 256) + align_up((size_t)B * Q * s * k * sizeof(int), 256);
+}
+
+extern "C" int pcst_knn_kernel_launches(int B, int Q, int R, int k, int self_query) {
+    if (B <= 0 || Q <= 0 || R <= 0 || k <= 0) return 0;
+    if (knn_use_grid(Q, R, self_query && Q == R)) return 10;  // bounding box, parameters, count, refine, count, scan, scatter, ring walk, listed sweep (+ memsets)
+    return knn_splits(B, Q, R) > 1 ? 2 : 1;
 }
 
 extern "C" int pcst_knn_f32(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx,
@@ -231,6 +277,14 @@ extern "C" int pcst_knn_f32(const float* query, const float* ref, int B, int Q, 
     PCST_CHECK_ARG(B > 0 && Q > 0 && R > 0, "B, Q, R must be positive");
     PCST_CHECK_ARG(B <= 65535, "B must be <= 65535");
     PCST_CHECK_ARG(k >= 1 && k <= kKnnMaxK && k <= R, "k must be in [1, min(16, R)]");
+    if (knn_use_grid(Q, R, query == ref && Q == R)) {
+        const size_t need_g = knn_grid_workspace_bytes(B, Q, R);
+        if (!ws || ws_bytes < need_g || ((uintptr_t)ws & 255)) {
+            set_error("pcst_knn_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need_g);
+            return PCST_ERR_WORKSPACE;
+        }
+        return knn_grid_run(query, ref, B, Q, R, k, idx, dist, ws, stream);
+    }
     int splits = knn_splits(B, Q, R);
     const int tiles = (R + kKnnTile - 1) / kKnnTile;
     const int tps = (tiles + splits - 1) / splits;

@@ -1,0 +1,384 @@
+// knn_grid.cu -- exact k nearest neighbours through a uniform grid over the reference cloud (sm_100a).
+//
+// The reference answers these queries with a kd-tree (sklearn NearestNeighbors: models/diffusion_model.py:146-147,
+// evaluation/metrics.py:126-127,152-153), i.e. it never evaluates all Q x R pairs; neither does this path.  The brute-force
+// sweep of knn.cu evaluates every pair (2.7e9 for the 90k x 30k interpolation) at 24-29 % of the FP32 peak; here:
+//   1. bounding box of the references (minmax kernel), cell edge h = cbrt(volume / R): about one reference per cell of the
+//      box, a dozen per OCCUPIED cell on LiDAR surfaces; per-cloud parameters stay on the device (no host round trip);
+//   2. counting sort of the references by cell: count -> exclusive scan -> scatter of (x, y, z, original index);
+//   3. one thread per query walks the cells in rings of growing Chebyshev radius r around its own cell and keeps the k best
+//      (distance, index) pairs; after ring r every unvisited reference is at least (r + w) * h away (w = the query's
+//      distance to the nearest wall of its own cell, in cells), so the walk stops as soon as the k-th best is closer.
+// Results are IDENTICAL to the brute-force kernel's (and so to sklearn's): distances are evaluated in fp64 in sklearn's
+// order with non-fused intrinsics, the list is ordered by (distance, index), which makes the visiting order irrelevant, and
+// the stopping bound carries a margin for the fp32 rounding of the cell coordinates.
+// Densities vary (LiDAR surfaces, Gaussian noise clouds of the sampling loop), so (a) the cell edge is refined on the device
+// from the measured occupancy: a first counting pass at h0 = cbrt(volume / R) yields the number of OCCUPIED cells, and when an
+// occupied cell holds more than a couple of references (a surface) the edge shrinks by sqrt(target / occupancy) before the
+// real pass; (b) the references are binned at THREE cell edges (h, 4h, 16h: one counting sort each, built by the same three
+// launches): a query that is not finished after kGridMaxRing rings at one level restarts at the next coarser one, so a
+// point in a sparse region pays 125 look-ups per level instead of a walk over thousands of empty fine cells; (c) a query
+// that no level finishes, or that has spent kGridBudget pair evaluations (a lone thread walking big coarse cells is slower
+// than the tiled sweep), is appended to a list, and the listed queries are answered by the tiled brute-force sweep of
+// knn.cu afterwards -- exactness never depends on the grid.
+// Bound: latency / L2 gather; tens of pair evaluations and 27-343 cell look-ups per query instead of R.
+#include "common.cuh"
+
+namespace pcst {
+
+constexpr int kGridLevels = 3;       // cell edge h, 4h, 16h
+constexpr int kGridMaxRing = 2;      // rings per level: (2 * 2 + 1)^3 = 125 cells, then the next (coarser) level
+constexpr float kGridTargetOcc = 2.0f;  // references per occupied cell the refinement aims at
+constexpr int kGridBudget = 1 << 30; // pair evaluations a query may spend in the grid before it is handed to the tiled sweep
+                                     // (off: with 1536 so many queries of a LiDAR scan overflow -- its near field packs
+                                     // hundreds of points into a cell -- that the listed sweep costs more than it saves)
+constexpr int kGridMaxDim = 1024;    // cells per axis
+
+struct GridParams {
+    float minx, miny, minz, inv_h, h;
+    int nx, ny, nz, ncell;
+};
+
+// one thread per cloud: grid geometry from the bounding box [min xyz, max xyz]
+__global__ void grid_params_kernel(const float* __restrict__ box, int B, int R, int cap, GridParams* __restrict__ gp) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* bx = box + (size_t)b * 6;
+    float ex = bx[3] - bx[0], ey = bx[4] - bx[1], ez = bx[5] - bx[2];
+    const float emax = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-20f));
+    // a flat or degenerate extent still spans one cell; its thickness must not drive the volume to zero
+    ex = fmaxf(ex, 1e-3f * emax); ey = fmaxf(ey, 1e-3f * emax); ez = fmaxf(ez, 1e-3f * emax);
+    float h = cbrtf(ex * ey * ez / (float)(R > 0 ? R : 1));
+    h = fmaxf(h, emax / (float)kGridMaxDim);
+    int nx, ny, nz;
+    for (;;) {
+        nx = min(kGridMaxDim, (int)(ex / h) + 1);
+        ny = min(kGridMaxDim, (int)(ey / h) + 1);
+        nz = min(kGridMaxDim, (int)(ez / h) + 1);
+        if ((long long)nx * ny * nz <= (long long)cap) break;
+        h *= 1.2599211f;
+    }
+    GridParams p;
+    p.minx = bx[0]; p.miny = bx[1]; p.minz = bx[2];
+    p.h = h; p.inv_h = 1.0f / h;
+    p.nx = nx; p.ny = ny; p.nz = nz; p.ncell = nx * ny * nz;
+    gp[b] = p;
+}
+
+__device__ __forceinline__ int grid_axis(float x, float mn, float inv_h, int n, float* frac) {
+    const float s = (x - mn) * inv_h;
+    int c = (int)floorf(s);
+    if (frac) *frac = s - (float)c;
+    if (c < 0) { c = 0; if (frac) *frac = -1.f; }          // outside the box: no wall distance may be credited
+    if (c > n - 1) { c = n - 1; if (frac) *frac = -1.f; }
+    return c;
+}
+__device__ __forceinline__ size_t grid_cell(const GridParams& p, float x, float y, float z) {
+    const int cx = grid_axis(x, p.minx, p.inv_h, p.nx, nullptr), cy = grid_axis(y, p.miny, p.inv_h, p.ny, nullptr),
+              cz = grid_axis(z, p.minz, p.inv_h, p.nz, nullptr);
+    return ((size_t)cz * p.ny + cy) * p.nx + cx;
+}
+
+// second look at the cell edge: `nocc` = occupied cells of the probing pass at h0.  Surfaces fill ~h^-2 cells, so an
+// occupancy of o references per occupied cell calls for h * sqrt(target / o); volumes (o ~ 1) keep their edge.  Then the
+// coarser levels: edge x 4 per level.  gp [B][kGridLevels].
+__global__ void grid_levels_kernel(const float* __restrict__ box, const int* __restrict__ nocc, int B, int R, int cap0,
+                                   const GridParams* __restrict__ probe, GridParams* __restrict__ gp) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    GridParams p = probe[b];
+    const float occ = (float)R / (float)max(nocc[b], 1);
+    const float* bx = box + (size_t)b * 6;
+    float ex = bx[3] - bx[0], ey = bx[4] - bx[1], ez = bx[5] - bx[2];
+    const float emax = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-20f));
+    ex = fmaxf(ex, 1e-3f * emax); ey = fmaxf(ey, 1e-3f * emax); ez = fmaxf(ez, 1e-3f * emax);
+    float h = p.h;
+    if (occ > 1.5f * kGridTargetOcc) h = fmaxf(h * sqrtf(kGridTargetOcc / occ), emax / (float)kGridMaxDim);
+    for (int l = 0; l < kGridLevels; ++l) {
+        const int cap = (cap0 >> (2 * l)) + 64;
+        int nx, ny, nz;
+        for (;;) {
+            nx = min(kGridMaxDim, (int)(ex / h) + 1);
+            ny = min(kGridMaxDim, (int)(ey / h) + 1);
+            nz = min(kGridMaxDim, (int)(ez / h) + 1);
+            if ((long long)nx * ny * nz <= (long long)cap) break;
+            h *= 1.2599211f;
+        }
+        p.h = h; p.inv_h = 1.0f / h;
+        p.nx = nx; p.ny = ny; p.nz = nz; p.ncell = nx * ny * nz;
+        gp[(size_t)b * kGridLevels + l] = p;
+        h *= 4.0f;
+    }
+}
+
+// probing pass: cell counts at h0 and the number of occupied cells
+__global__ void grid_probe_kernel(const float* __restrict__ ref, int R, int cap, const GridParams* __restrict__ probe,
+                                  int* __restrict__ counts, int* __restrict__ nocc) {
+    const int b = blockIdx.y;
+    const GridParams p = probe[b];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < R; j += gridDim.x * blockDim.x) {
+        const float* q = ref + ((size_t)b * R + j) * 3;
+        if (atomicAdd(&counts[(size_t)b * cap + grid_cell(p, q[0], q[1], q[2])], 1) == 0) atomicAdd(&nocc[b], 1);
+    }
+}
+
+struct GridArrays {  // per level: row stride of the cell arrays, and the arrays themselves
+    int cap[kGridLevels];
+    int* counts[kGridLevels];
+    int* fill[kGridLevels];
+    int* starts[kGridLevels];
+    float4* sorted[kGridLevels];
+};
+
+__global__ void grid_count_kernel(const float* __restrict__ ref, int R, const GridParams* __restrict__ gp, GridArrays ga) {
+    const int b = blockIdx.y;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < R; j += gridDim.x * blockDim.x) {
+        const float* q = ref + ((size_t)b * R + j) * 3;
+        const float x = q[0], y = q[1], z = q[2];
+#pragma unroll
+        for (int l = 0; l < kGridLevels; ++l)
+            atomicAdd(&ga.counts[l][(size_t)b * ga.cap[l] + grid_cell(gp[(size_t)b * kGridLevels + l], x, y, z)], 1);
+    }
+}
+
+// exclusive scan of one cloud's cell counts at one level: one CTA of 1024 threads, each owning a contiguous run of cells
+__global__ void __launch_bounds__(1024)
+grid_scan_kernel(const GridParams* __restrict__ gp, GridArrays ga) {
+    __shared__ int part[1024];
+    const int b = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
+    const int n = gp[(size_t)b * kGridLevels + l].ncell;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, t * per), hi = min(n, lo + per);
+    const int* c = ga.counts[l] + (size_t)b * ga.cap[l];
+    int* s = ga.starts[l] + (size_t)b * ga.cap[l];
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += c[i];
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+        const int v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - sum;
+    for (int i = lo; i < hi; ++i) {
+        s[i] = run;
+        run += c[i];
+    }
+}
+
+__global__ void grid_scatter_kernel(const float* __restrict__ ref, int R, const GridParams* __restrict__ gp, GridArrays ga) {
+    const int b = blockIdx.y;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < R; j += gridDim.x * blockDim.x) {
+        const float* q = ref + ((size_t)b * R + j) * 3;
+        const float x = q[0], y = q[1], z = q[2];
+#pragma unroll
+        for (int l = 0; l < kGridLevels; ++l) {
+            const size_t cell = (size_t)b * ga.cap[l] + grid_cell(gp[(size_t)b * kGridLevels + l], x, y, z);
+            const int pos = ga.starts[l][cell] + atomicAdd(&ga.fill[l][cell], 1);
+            ga.sorted[l][(size_t)b * R + pos] = make_float4(x, y, z, __int_as_float(j));
+        }
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+grid_query_kernel(const float* __restrict__ query, int Q, int R, int k, const GridParams* __restrict__ gp, GridArrays ga,
+                  int64_t* __restrict__ idx, double* __restrict__ dist, int* __restrict__ qlist, int* __restrict__ qcount) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const float* qp = query + ((size_t)b * Q + q) * 3;
+    const float fx = qp[0], fy = qp[1], fz = qp[2];
+    const double qx = fx, qy = fy, qz = fz;
+
+    double bd[KMAX];
+    int bi[KMAX];
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) {
+        bd[t] = __longlong_as_double(0x7ff0000000000000ll);
+        bi[t] = 0x7fffffff;
+    }
+    auto consider = [&](const float4 c) {
+        const int j = __float_as_int(c.w);
+        const double dx = __dsub_rn(qx, (double)c.x), dy = __dsub_rn(qy, (double)c.y), dz = __dsub_rn(qz, (double)c.z);
+        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (d < bd[KMAX - 1] || (d == bd[KMAX - 1] && j < bi[KMAX - 1])) {
+            double cd = d;
+            int ci = j;
+#pragma unroll
+            for (int u = 0; u < KMAX; ++u) {
+                if (cd < bd[u] || (cd == bd[u] && ci < bi[u])) {   // ordered by (distance, index): visiting order is irrelevant
+                    const double td = bd[u];
+                    const int ti = bi[u];
+                    bd[u] = cd;
+                    bi[u] = ci;
+                    cd = td;
+                    ci = ti;
+                }
+            }
+        }
+    };
+    auto kth = [&]() {  // the k-th entry of the KMAX-list
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u)
+            if (u == k - 1) v = bd[u];
+        return v;
+    };
+    auto wall = [](float f) { return f < 0.f ? 0.f : fminf(f, 1.f - f); };
+
+    bool done = false;
+    int spent = 0;  // pair evaluations so far: a thread walking big coarse cells alone is slower than the tiled sweep
+    for (int l = 0; l < kGridLevels && !done && spent <= kGridBudget; ++l) {
+        const GridParams p = gp[(size_t)b * kGridLevels + l];
+        const int* st = ga.starts[l] + (size_t)b * ga.cap[l];
+        const int* ct = ga.counts[l] + (size_t)b * ga.cap[l];
+        const float4* pts = ga.sorted[l] + (size_t)b * R;
+        // a coarser level revisits what the finer one saw: start its list afresh
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+            bd[t] = __longlong_as_double(0x7ff0000000000000ll);
+            bi[t] = 0x7fffffff;
+        }
+        auto scan_cell = [&](int x, int y, int z) {
+            const size_t cell = ((size_t)z * p.ny + y) * p.nx + x;
+            const int n = __ldg(ct + cell);
+            if (n == 0 || spent > kGridBudget) return;
+            spent += n;
+            const float4* c = pts + __ldg(st + cell);
+            for (int t = 0; t < n; ++t) consider(__ldg(c + t));
+        };
+        float wx, wy, wz;
+        const int cx = grid_axis(fx, p.minx, p.inv_h, p.nx, &wx), cy = grid_axis(fy, p.miny, p.inv_h, p.ny, &wy),
+                  cz = grid_axis(fz, p.minz, p.inv_h, p.nz, &wz);
+        // distance (in cells) from the query to the nearest wall of its own cell; 0 when it lies outside the box on that axis
+        const float w = fminf(fminf(wall(wx), wall(wy)), wall(wz));
+        const int rmax = max(max(max(cx, p.nx - 1 - cx), max(cy, p.ny - 1 - cy)), max(cz, p.nz - 1 - cz));
+        for (int r = 0; r <= min(rmax, kGridMaxRing); ++r) {
+            const int z0 = max(0, cz - r), z1 = min(p.nz - 1, cz + r);
+            const int y0 = max(0, cy - r), y1 = min(p.ny - 1, cy + r);
+            const int x0 = max(0, cx - r), x1 = min(p.nx - 1, cx + r);
+            for (int z = z0; z <= z1; ++z) {
+                const bool zface = (z == cz - r) || (z == cz + r);
+                for (int y = y0; y <= y1; ++y) {
+                    const bool yface = (y == cy - r) || (y == cy + r);
+                    if (zface || yface) {
+                        for (int x = x0; x <= x1; ++x) scan_cell(x, y, z);
+                    } else {  // interior rows of the shell: only the two end cells belong to ring r
+                        if (cx - r >= 0) scan_cell(cx - r, y, z);
+                        if (r > 0 && cx + r <= p.nx - 1) scan_cell(cx + r, y, z);
+                    }
+                }
+            }
+            // every reference outside the visited cube is farther than (r + w) cells; 4e-3 of a cell covers the fp32
+            // rounding of the cell coordinates of the query and of the references (|scaled coordinate| <= 1024)
+            const double reach = (double)fmaxf((float)r + w - 4e-3f, 0.f) * (double)p.h;
+            if (spent > kGridBudget) break;             // over budget: cells may have been left out, the list is not final
+            if (kth() <= reach * reach || r == rmax) {  // r == rmax: the whole grid has been visited
+                done = true;
+                break;
+            }
+        }
+    }
+    if (!done) {
+        // the ring budget of every level is spent (a query far from all references): hand it to the tiled sweep
+        qlist[(size_t)b * Q + atomicAdd(&qcount[b], 1)] = q;
+        return;
+    }
+    for (int t = 0; t < k; ++t) {
+        double v = 0.0;
+        int j = 0;
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u)
+            if (u == t) { v = bd[u]; j = bi[u]; }
+        idx[((size_t)b * Q + q) * k + t] = j;
+        dist[((size_t)b * Q + q) * k + t] = __dsqrt_rn(v);
+    }
+}
+
+// workspace: box | probe params | level params | nocc | qcount | per level (counts, fill, starts) | per level sorted | qlist
+struct GridWs {
+    size_t box, probe, params, nocc, qcount, cells, cells_end, sorted[kGridLevels], qlist, total;
+    size_t counts[kGridLevels], fill[kGridLevels], starts[kGridLevels];
+    int cap0, cap[kGridLevels];
+};
+static GridWs grid_ws(int B, int Q, int R) {
+    GridWs w;
+    w.cap0 = 24 * R + 64;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes, 256); return o; };
+    w.box = take((size_t)B * 6 * sizeof(float));
+    w.probe = take((size_t)B * sizeof(GridParams));
+    w.params = take((size_t)B * kGridLevels * sizeof(GridParams));
+    w.nocc = take((size_t)B * sizeof(int));
+    w.qcount = take((size_t)B * sizeof(int));
+    w.cells = off;
+    for (int l = 0; l < kGridLevels; ++l) {
+        w.cap[l] = (w.cap0 >> (2 * l)) + 64;
+        w.counts[l] = take((size_t)B * w.cap[l] * sizeof(int));
+        w.fill[l] = take((size_t)B * w.cap[l] * sizeof(int));
+    }
+    w.cells_end = off;
+    for (int l = 0; l < kGridLevels; ++l) w.starts[l] = take((size_t)B * w.cap[l] * sizeof(int));
+    for (int l = 0; l < kGridLevels; ++l) w.sorted[l] = take((size_t)B * R * sizeof(float4));
+    w.qlist = take((size_t)B * Q * sizeof(int));
+    w.total = off;
+    return w;
+}
+
+size_t knn_grid_workspace_bytes(int B, int Q, int R) { return grid_ws(B, Q, R).total; }
+
+int knn_sweep_listed(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist,
+                     const int* qlist, const int* qcount, cudaStream_t stream);
+
+int knn_grid_run(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist, void* ws,
+                 cudaStream_t stream) {
+    const GridWs w = grid_ws(B, Q, R);
+    char* base = (char*)ws;
+    float* box = (float*)(base + w.box);
+    GridParams* probe = (GridParams*)(base + w.probe);
+    GridParams* gp = (GridParams*)(base + w.params);
+    int* nocc = (int*)(base + w.nocc);
+    int* qcount = (int*)(base + w.qcount);
+    int* qlist = (int*)(base + w.qlist);
+    GridArrays ga;
+    for (int l = 0; l < kGridLevels; ++l) {
+        ga.cap[l] = w.cap[l];
+        ga.counts[l] = (int*)(base + w.counts[l]);
+        ga.fill[l] = (int*)(base + w.fill[l]);
+        ga.starts[l] = (int*)(base + w.starts[l]);
+        ga.sorted[l] = (float4*)(base + w.sorted[l]);
+    }
+    int st = pcst_minmax_f32(ref, B, R, box, (pcst_stream_t)stream);
+    if (st != PCST_OK) return st;
+    // probing pass at h0 = cbrt(volume / R) (at most 2R + 64 cells, counted in level 0's array)
+    PCST_CUDA(cudaMemsetAsync(nocc, 0, w.cells - w.nocc, stream));                                // nocc and qcount
+    PCST_CUDA(cudaMemsetAsync(ga.counts[0], 0, (size_t)B * w.cap[0] * sizeof(int), stream));
+    grid_params_kernel<<<(B + 63) / 64, 64, 0, stream>>>(box, B, R, 2 * R + 64, probe);
+    PCST_CUDA(cudaGetLastError());
+    int blocks = (R + 255) / 256;
+    if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
+    grid_probe_kernel<<<dim3(blocks, B), 256, 0, stream>>>(ref, R, w.cap[0], probe, ga.counts[0], nocc);
+    PCST_CUDA(cudaGetLastError());
+    grid_levels_kernel<<<(B + 63) / 64, 64, 0, stream>>>(box, nocc, B, R, w.cap0, probe, gp);
+    PCST_CUDA(cudaGetLastError());
+    // the real passes, all levels at once
+    PCST_CUDA(cudaMemsetAsync(base + w.cells, 0, w.cells_end - w.cells, stream));                 // counts and fill of every level
+    grid_count_kernel<<<dim3(blocks, B), 256, 0, stream>>>(ref, R, gp, ga);
+    PCST_CUDA(cudaGetLastError());
+    grid_scan_kernel<<<dim3(B, kGridLevels), 1024, 0, stream>>>(gp, ga);
+    PCST_CUDA(cudaGetLastError());
+    grid_scatter_kernel<<<dim3(blocks, B), 256, 0, stream>>>(ref, R, gp, ga);
+    PCST_CUDA(cudaGetLastError());
+    dim3 grid((Q + 127) / 128, B);
+    if (k <= 1) grid_query_kernel<1><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
+    else if (k <= 4) grid_query_kernel<4><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
+    else if (k <= 9) grid_query_kernel<9><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
+    else grid_query_kernel<16><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
+    PCST_CUDA(cudaGetLastError());
+    return knn_sweep_listed(query, ref, B, Q, R, k, idx, dist, qlist, qcount, stream);
+}
+
+}  // namespace pcst

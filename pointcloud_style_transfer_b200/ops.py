@@ -486,9 +486,8 @@ def knn(query: Tensor, ref: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     with torch.cuda.device(query.device):
         nb = lib.pcst_knn_workspace_bytes(B, Q, R, k)
         ws = _workspace(nb, query.device)
-        # a non-empty workspace = the reference range is split over CTAs: sweep + merge kernel
         _call("pcst_knn_f32", _p(query), _p(ref), B, Q, R, k, _p(idx), _p(dist), _p(ws), ws.numel(), _stream(),
-              kernels=2 if nb > 0 else 1)
+              kernels=int(lib.pcst_knn_kernel_launches(B, Q, R, k, int(query.data_ptr() == ref.data_ptr()))))
     return dist, idx
 
 

@@ -1146,6 +1146,47 @@ def test_upsample_knn_full_size_against_oracle_subset(api, dev, oracle):
     np.testing.assert_allclose(out[0, unk], ref, rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("case", ["uniform", "lidar", "lattice_ties", "outliers", "flat", "degenerate", "tiny_k16"])
+def test_knn_grid_search_is_identical_to_the_sweep(api, dev, oracle, case):
+    """The exact uniform-grid search (csrc/knn_grid.cu), forced on for small clouds: indices AND fp64 distances identical
+    to the oracle (sklearn's order; ties to the lower index) -- exact ties on a lattice, queries far outside the
+    reference box (ring walk cut off -> full scan), a flat cloud (one cell thick), all references in one point."""
+    from pointcloud_style_transfer_b200 import _lib
+
+    k = 3
+    if case == "uniform":
+        q, r, k = S.uniform_cloud(1, 2, 3000).numpy(), S.uniform_cloud(2, 2, 5000).numpy(), 9
+    elif case == "lidar":
+        x = S.lidar_scan(6, 12000).numpy()
+        q, r = x[:, ::2].copy(), x[:, 1::3].copy()
+    elif case == "lattice_ties":
+        q = S.lattice(S.uniform_cloud(3, 1, 2000), 16).numpy()
+        r, k = S.lattice(S.uniform_cloud(4, 1, 4000), 16).numpy(), 4
+    elif case == "outliers":
+        r = S.uniform_cloud(5, 1, 4000).numpy() * 0.2
+        q = np.concatenate([S.uniform_cloud(6, 1, 500).numpy() * 0.2, S.uniform_cloud(7, 1, 500).numpy() * 5 + 3], 1)
+    elif case == "flat":
+        r = S.uniform_cloud(8, 1, 4000).numpy()
+        r[..., 2] = 0.25
+        q = S.uniform_cloud(9, 1, 1000).numpy()
+    elif case == "degenerate":
+        r = np.full((1, 300, 3), 0.5, np.float32)
+        q, k = S.uniform_cloud(10, 1, 200).numpy(), 5
+    else:
+        q, r, k = S.uniform_cloud(11, 1, 257).numpy(), S.uniform_cloud(12, 1, 100).numpy(), 16
+    _lib.set_tuning("knn.grid", 1)
+    try:
+        dist, idx = api.ops.knn(torch.from_numpy(q).to(dev), torch.from_numpy(r).to(dev), k)
+    finally:
+        _lib.set_tuning("knn.grid", 0)
+    rd, ri = oracle.knn(q, r, k)
+    assert np.array_equal(dist.cpu().numpy(), rd)
+    if case in ("lattice_ties", "degenerate"):
+        assert np.array_equal(idx.cpu().numpy(), ri)          # exact ties: lowest indices, in index order
+    else:
+        assert np.array_equal(idx.cpu().numpy(), ri)
+
+
 def test_upsample_knn_golden(api, dev, golden, oracle):
     g = golden("upsample_knn")
     hp = api.dm.HierarchicalProcessor(6000, 1500)
