@@ -239,6 +239,19 @@ int pcst_chamfer_bwd_f32(const float* pred, const float* target, const int64_t* 
                          const int64_t* arg_tp, const float* grad_out, int B, int N, int M,
                          float* grad_pred, float* grad_target, pcst_stream_t stream);
 
+/* ---- query-sharded Chamfer (multi-GPU): the kernels either side of its single collective ----------------
+ * Rank r sweeps its [n_r x M] tile of the pair matrix with pcst_nn_min_pair_f32 (complete row minima of its queries, partial
+ * column minima of all M targets).  _pack writes payload [B, P] with P = pcst_chamfer_shard_payload_floats(M) = M + 64:
+ * colmin | 32 fp64 partial row sums (float pairs); the ranks all-gather the payloads ([G, B, P]); _finish forms
+ * out [B] = sum_r rowsum_r / n_total + sum_m min_r colmin_r[m] / M (x 0.5 for form 1, the metric), fp64 sums added in a
+ * fixed order: identical on every rank.  ws: B * 32 doubles, 256-byte aligned.
+ * Replaces all_reduce(MIN) + all_reduce(SUM) + host-side reductions around models/losses.py:61 / evaluation/metrics.py:42. */
+int pcst_chamfer_shard_payload_floats(int M);
+int pcst_chamfer_shard_pack_f32(const float* rowmin, const float* colmin, int B, int n, int M, float* payload,
+                                pcst_stream_t stream);
+int pcst_chamfer_shard_finish_f32(const float* gathered, int G, int B, int M, long long n_total, int form, float* out, void* ws,
+                                  size_t ws_bytes, pcst_stream_t stream);
+
 /* ---- k nearest neighbours: sklearn NearestNeighbors(n_neighbors=k).kneighbors ------------------
  * call sites models/diffusion_model.py:146-147, evaluation/metrics.py:126-127,152-153.
  * query [B,Q,3], ref [B,R,3] fp32 -> idx [B,Q,k] int64, dist [B,Q,k] fp64 ascending (Euclidean);

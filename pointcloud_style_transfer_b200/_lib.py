@@ -101,6 +101,10 @@ SIGNATURES = {
                                          c_void_p, c_size_t, c_void_p]),
     "pcst_chamfer_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                      c_void_p, c_void_p]),
+    "pcst_chamfer_shard_pack_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pcst_chamfer_shard_payload_floats": (c_int, [c_int]),
+    "pcst_chamfer_shard_finish_f32": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.c_longlong, c_int, c_void_p, c_void_p,
+                                              c_size_t, c_void_p]),
     "pcst_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pcst_knn_kernel_launches": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "pcst_knn_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,

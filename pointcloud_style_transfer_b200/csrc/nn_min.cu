@@ -791,3 +791,111 @@ extern "C" int pcst_chamfer_bwd_f32(const float* pred, const float* target, cons
                                                              grad_target);
     return check_cuda(cudaGetLastError(), "chamfer_bwd_kernel");
 }
+
+// ---- query-sharded Chamfer: the small kernels either side of its single collective --------------------------------------
+// (SURVEY.md 8(e) variant 2.)  Rank r has swept its [n_r x M] tile: complete row minima of its n_r queries, PARTIAL column
+// minima of all M targets.  Instead of all_reduce(MIN) of the columns + all_reduce(SUM) of the row sums + host-side glue:
+//   pack   : payload[b] = colmin[b, 0..M) | kShardParts fp64 partial sums of rowmin[b, :]      -> ONE all-gather of payloads
+//   finish : out[b] = sum_r rowsum_r / N  +  sum_m min_r colmin_r[m] / M       (fp64 sums, / 2 for the metric form)
+// Both are spread over many CTAs (a 120k-column row is 480 KB) and deterministic: partial sums are written to fixed slots
+// and added in a fixed order, so every rank gets the same bits.
+namespace pcst {
+
+constexpr int kShardParts = 32;   // CTAs per batch element in pack / finish = fp64 partial sums per rank and element
+constexpr int kShardThreads = 256;
+
+__device__ __forceinline__ double block_sum_f64(double s, double* part) {
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+    return tot;  // valid in thread 0
+}
+
+// payload row: M floats (column minima), then kShardParts doubles stored as float pairs (row stride M + 2 * kShardParts)
+__global__ void __launch_bounds__(kShardThreads)
+chamfer_shard_pack_kernel(const float* __restrict__ rowmin, const float* __restrict__ colmin, int n, int M,
+                          float* __restrict__ payload) {
+    __shared__ double part[kShardThreads / 32];
+    const int b = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
+    const int stride = M + 2 * kShardParts;
+    float* out = payload + (size_t)b * stride;
+    const float* cm = colmin + (size_t)b * M;
+    for (int m = c * kShardThreads + t; m < M; m += kShardParts * kShardThreads) out[m] = cm[m];
+    double s = 0.0;
+    const float* rm = rowmin + (size_t)b * n;
+    for (int i = c * kShardThreads + t; i < n; i += kShardParts * kShardThreads) s += (double)rm[i];
+    const double tot = block_sum_f64(s, part);
+    if (t == 0) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(tot);
+        out[M + 2 * c] = __uint_as_float((unsigned)(bits & 0xffffffffull));
+        out[M + 2 * c + 1] = __uint_as_float((unsigned)(bits >> 32));
+    }
+}
+
+// stage 1: CTA c of element b: min over the G ranks of its column slice, fp64 sum -> colpart[b][c]
+__global__ void __launch_bounds__(kShardThreads)
+chamfer_shard_colmin_kernel(const float* __restrict__ gathered, int G, int B, int M, double* __restrict__ colpart) {
+    __shared__ double part[kShardThreads / 32];
+    const int b = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
+    const size_t stride = (size_t)B * (M + 2 * kShardParts);
+    const float* base = gathered + (size_t)b * (M + 2 * kShardParts);
+    double s = 0.0;
+    for (int m = c * kShardThreads + t; m < M; m += kShardParts * kShardThreads) {
+        float v = base[m];
+        for (int g = 1; g < G; ++g) v = fminf(v, base[(size_t)g * stride + m]);
+        s += (double)v;
+    }
+    const double tot = block_sum_f64(s, part);
+    if (t == 0) colpart[(size_t)b * kShardParts + c] = tot;
+}
+
+// stage 2: one warp per element adds the column partials and the G x kShardParts row partials in a fixed order
+__global__ void chamfer_shard_finish_kernel(const float* __restrict__ gathered, const double* __restrict__ colpart, int G, int B,
+                                            int M, double n_total, int form, float* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const size_t stride = (size_t)B * (M + 2 * kShardParts);
+    double cols = 0.0, rows = 0.0;
+    for (int c = 0; c < kShardParts; ++c) cols += colpart[(size_t)b * kShardParts + c];
+    for (int g = 0; g < G; ++g) {
+        const float* p = gathered + (size_t)g * stride + (size_t)b * (M + 2 * kShardParts) + M;
+        for (int c = 0; c < kShardParts; ++c) {
+            const unsigned long long bits = (unsigned long long)__float_as_uint(p[2 * c]) | ((unsigned long long)__float_as_uint(p[2 * c + 1]) << 32);
+            rows += __longlong_as_double((long long)bits);
+        }
+    }
+    double v = rows / n_total + cols / (double)M;
+    if (form != 0) v *= 0.5;
+    out[b] = (float)v;
+}
+
+}  // namespace pcst
+
+extern "C" int pcst_chamfer_shard_payload_floats(int M) { return M > 0 ? M + 2 * pcst::kShardParts : 0; }
+
+extern "C" int pcst_chamfer_shard_pack_f32(const float* rowmin, const float* colmin, int B, int n, int M, float* payload,
+                                           pcst_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCST_CHECK_ARG(colmin && payload && (rowmin || n == 0), "null pointer");
+    PCST_CHECK_ARG(B > 0 && B <= 65535 && n >= 0 && M > 0, "bad sizes");
+    chamfer_shard_pack_kernel<<<dim3(kShardParts, B), kShardThreads, 0, stream>>>(rowmin, colmin, n, M, payload);
+    return check_cuda(cudaGetLastError(), "chamfer_shard_pack_kernel");
+}
+
+extern "C" int pcst_chamfer_shard_finish_f32(const float* gathered, int G, int B, int M, long long n_total, int form, float* out,
+                                             void* ws, size_t ws_bytes, pcst_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCST_CHECK_ARG(gathered && out && ws, "null pointer");
+    PCST_CHECK_ARG(G > 0 && B > 0 && B <= 65535 && M > 0 && n_total > 0, "bad sizes");
+    if (ws_bytes < (size_t)B * kShardParts * sizeof(double) || ((uintptr_t)ws & 255)) {
+        set_error("pcst_chamfer_shard_finish_f32: workspace too small or misaligned (needs B * 32 doubles)");
+        return PCST_ERR_WORKSPACE;
+    }
+    chamfer_shard_colmin_kernel<<<dim3(kShardParts, B), kShardThreads, 0, stream>>>(gathered, G, B, M, (double*)ws);
+    PCST_CUDA(cudaGetLastError());
+    chamfer_shard_finish_kernel<<<(B + 63) / 64, 64, 0, stream>>>(gathered, (const double*)ws, G, B, M, (double)n_total, form, out);
+    return check_cuda(cudaGetLastError(), "chamfer_shard_finish_kernel");
+}

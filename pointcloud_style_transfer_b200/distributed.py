@@ -128,6 +128,84 @@ def chamfer_query_sharded_one_sweep(pred_local: torch.Tensor, target_local: torc
     return out.float()
 
 
+def _default_pack(rowmin, colmin):
+    from . import ops
+    return ops.chamfer_shard_pack(rowmin, colmin)
+
+
+def _default_finish(gathered, n_total, form):
+    from . import ops
+    return ops.chamfer_shard_finish(gathered, n_total, form)
+
+
+def chamfer_query_sharded_fused(pred_local: torch.Tensor, target_local: torch.Tensor, pred_total: int, target_total: int,
+                                group=None, form: int = 0, pair_fn: Optional[Callable] = None,
+                                pack_fn: Optional[Callable] = None, finish_fn: Optional[Callable] = None) -> torch.Tensor:
+    """``chamfer_query_sharded_one_sweep`` with ONE result collective and no host-side arithmetic: all-gather of the target
+    cloud -> one sweep of the local [n_r x M] tile -> pack (column minima | fp64 row sum) -> all-gather of the payloads
+    -> finish (min over ranks, fp64 sums, the two means) -> [B], identical on every rank.  Shards must be the
+    ``slice_of_rank`` partitions of ``pred_total`` / ``target_total`` (no size exchange, no synchronisation): the whole
+    call is stream-ordered and can be captured in a CUDA graph (``GraphedShardedChamfer``)."""
+    pair_fn, pack_fn, finish_fn = pair_fn or _default_nn_min_pair, pack_fn or _default_pack, finish_fn or _default_finish
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    target_all = all_gather_ragged(target_local, group, target_total) if world > 1 else target_local
+    B, M = target_all.shape[0], target_all.shape[1]
+    if pred_local.shape[1] > 0:
+        rowmin, colmin = pair_fn(pred_local, target_all, 0 if form == 0 else 1)
+    else:   # an empty query slice: no row minima, column minima at +inf
+        rowmin = target_all.new_zeros(B, 0)
+        colmin = torch.full((B, M), float("inf"), dtype=torch.float32, device=target_all.device)
+    payload = pack_fn(rowmin, colmin)                                   # [B, P]: column minima | fp64 row-sum partials
+    P = payload.shape[1]
+    if world > 1:
+        gathered = payload.new_empty(world * B, P)                     # ranks concatenated along dim 0
+        dist.all_gather_into_tensor(gathered, payload.contiguous(), group=group)
+        gathered = gathered.view(world, B, P)
+    else:
+        gathered = payload[None]
+    return finish_fn(gathered, pred_total, form)
+
+
+class GraphedShardedChamfer:
+    """The fused query-sharded Chamfer captured into ONE CUDA graph per shape (both collectives included): a call is two
+    device-to-device copies of the local shards into the graph's static buffers and a graph launch, so that the ~20 kernel /
+    collective launches of the call no longer cost host time between them."""
+
+    def __init__(self, pred_total: int, target_total: int, group=None, form: int = 0):
+        self.pred_total, self.target_total, self.group, self.form = pred_total, target_total, group, form
+        self._state = {}
+
+    def __call__(self, pred_local: torch.Tensor, target_local: torch.Tensor) -> torch.Tensor:
+        key = (tuple(pred_local.shape), tuple(target_local.shape), pred_local.device)
+        st = self._state.get(key)
+        if st is None:
+            st = {"p": torch.empty_like(pred_local), "t": torch.empty_like(target_local)}
+            st["p"].copy_(pred_local)
+            st["t"].copy_(target_local)
+            run = lambda: chamfer_query_sharded_fused(st["p"], st["t"], self.pred_total, self.target_total, self.group, self.form)
+            side = torch.cuda.Stream(device=pred_local.device)
+            side.wait_stream(torch.cuda.current_stream(pred_local.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(3):
+                    run()
+            torch.cuda.current_stream(pred_local.device).wait_stream(side)
+            torch.cuda.synchronize(pred_local.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g), torch.no_grad():
+                st["out"] = run()
+            st["graph"] = g
+            self._state[key] = st
+        st["p"].copy_(pred_local, non_blocking=True)
+        st["t"].copy_(target_local, non_blocking=True)
+        st["graph"].replay()
+        return st["out"]
+
+    def release(self) -> None:
+        """Drop the captured graphs (they hold NCCL kernels): call before ``destroy_process_group``."""
+        torch.cuda.synchronize()
+        self._state.clear()
+
+
 def _default_knn(q, r, k):
     from . import ops
     return ops.knn(q, r, k)

@@ -756,3 +756,38 @@ def noise_predictor(points: Tensor, timestep: Tensor, style: Tensor, packed: Ten
 @noise_predictor.register_fake
 def _(points, timestep, style, packed, feature_dim, time_dim, nblocks):
     return points.new_empty(points.shape[0], points.shape[1], 3, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------- query-sharded Chamfer: pack / finish kernels
+
+KERNELS_PER_CALL["pcst_chamfer_shard_pack_f32"] = 1
+KERNELS_PER_CALL["pcst_chamfer_shard_finish_f32"] = 1
+
+
+def chamfer_shard_pack(rowmin: Tensor, colmin: Tensor) -> Tensor:
+    """rowmin [B,n] (this rank's complete row minima), colmin [B,M] (partial column minima) -> payload [B, M + 64] fp32 =
+    colmin | 32 fp64 partial row sums as float pairs: what the ranks all-gather."""
+    lib = _lib.load()
+    _need_cuda(rowmin, colmin)
+    rowmin, colmin = _f32c(rowmin), _f32c(colmin)
+    B, M = colmin.shape
+    n = rowmin.shape[1]
+    payload = torch.empty(B, lib.pcst_chamfer_shard_payload_floats(M), dtype=torch.float32, device=colmin.device)
+    with torch.cuda.device(colmin.device):
+        _call("pcst_chamfer_shard_pack_f32", _p(rowmin), _p(colmin), B, n, M, _p(payload), _stream())
+    return payload
+
+
+def chamfer_shard_finish(gathered: Tensor, n_total: int, form: int) -> Tensor:
+    """gathered [G, B, M + 64] (the all-gathered payloads) -> chamfer [B] fp32 (identical on every rank)."""
+    lib = _lib.load()
+    _need_cuda(gathered)
+    gathered = _f32c(gathered)
+    G, B, P = gathered.shape
+    M = P - (lib.pcst_chamfer_shard_payload_floats(1) - 1)
+    out = torch.empty(B, dtype=torch.float32, device=gathered.device)
+    with torch.cuda.device(gathered.device):
+        ws = _workspace(B * 32 * 8, gathered.device)
+        _call("pcst_chamfer_shard_finish_f32", _p(gathered), G, B, M, int(n_total), int(form), _p(out), _p(ws), ws.numel(),
+              _stream(), kernels=2)
+    return out

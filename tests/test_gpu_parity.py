@@ -1082,6 +1082,21 @@ def test_diffusion_loss_call_site(api, dev, oracle):
     assert set(L(pn, an)[1]) == {"noise_loss", "total_loss"}
 
 
+def test_sharded_chamfer_pack_finish_equals_single_sweep(api, dev):
+    """The two kernels around the single collective of the query-sharded Chamfer: splitting the queries into G slices,
+    packing each slice's (column minima | fp64 row sum) and finishing over the stacked payloads gives the one-GPU value
+    (the collective itself is an all-gather; here the payloads are stacked locally)."""
+    p, t = S.lidar_scan(0, 9000).to(dev), S.lidar_scan(100, 7000).to(dev)
+    for form, ref in ((0, api.losses.chamfer_distance_chunked_optimized(p, t)),
+                      (1, api.Metrics("cuda").chamfer_distance(p, t))):
+        payloads = []
+        for lo, hi in ((0, 3000), (3000, 3001), (3001, 9000)):
+            rowmin, colmin = api.ops.nn_min_pair(p[:, lo:hi].contiguous(), t, 0 if form == 0 else 1)
+            payloads.append(api.ops.chamfer_shard_pack(rowmin, colmin))
+        out = api.ops.chamfer_shard_finish(torch.stack(payloads), 9000, form)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-6)
+
+
 # ------------------------------------------------------------------------------- kNN / upsample
 
 

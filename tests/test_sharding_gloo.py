@@ -37,6 +37,29 @@ def _oracle_knn(q, r, k):
     return torch.from_numpy(d), torch.from_numpy(i)
 
 
+_PARTS = 32  # fp64 partial row sums per payload row (pcst_chamfer_shard_payload_floats(M) - M = 64 float slots)
+
+
+def _cpu_pack(rowmin, colmin):
+    """CPU stand-in of pcst_chamfer_shard_pack_f32: colmin | 32 fp64 partial row sums as float pairs."""
+    B, M = colmin.shape
+    out = np.zeros((B, M + 2 * _PARTS), np.float32)
+    out[:, :M] = colmin.numpy()
+    parts = np.zeros((B, _PARTS), np.float64)
+    parts[:, 0] = rowmin.numpy().astype(np.float64).sum(axis=1) if rowmin.shape[1] else 0.0
+    out[:, M:] = parts.view(np.float32)
+    return torch.from_numpy(out)
+
+
+def _cpu_finish(gathered, n_total, form):
+    g = gathered.numpy()
+    M = g.shape[2] - 2 * _PARTS
+    cols = g[:, :, :M].min(axis=0).astype(np.float64).sum(axis=1)
+    rows = np.ascontiguousarray(g[:, :, M:]).view(np.float64).sum(axis=(0, 2))
+    v = rows / n_total + cols / M
+    return torch.from_numpy((v / 2 if form else v).astype(np.float32))
+
+
 class _ToyEncoder(torch.nn.Module):
     def forward(self, x):  # [S,N,3] -> [S,4]: any per-scan function will do for the plumbing test
         return torch.cat([x.mean(dim=1), x.abs().amax(dim=(1, 2))[:, None]], dim=1)
@@ -57,6 +80,11 @@ def _worker(rank, world, port, q):
         cd1 = D.chamfer_query_sharded_one_sweep(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair)
         cdm1 = D.chamfer_query_sharded_one_sweep(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair, form=1,
                                                  pred_total=1001, target_total=777)  # known totals: no size exchange
+        # the fused variant: one result collective (all-gather of packed payloads), pack / finish injected
+        cdf = D.chamfer_query_sharded_fused(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), 1001, 777,
+                                            pair_fn=_oracle_pair, pack_fn=_cpu_pack, finish_fn=_cpu_finish)
+        cdfm = D.chamfer_query_sharded_fused(pred[:, lo:hi].contiguous(), target[:, lo2:hi2].contiguous(), 1001, 777, form=1,
+                                             pair_fn=_oracle_pair, pack_fn=_cpu_pack, finish_fn=_cpu_finish)
         # a rank with an EMPTY query slice (more ranks than points would do this): rank 1 holds no pred points
         elo, ehi = (0, 5) if rank == 0 else (5, 5)
         cde = D.chamfer_query_sharded_one_sweep(pred[:, :5][:, elo:ehi].contiguous(), target[:, lo2:hi2].contiguous(), pair_fn=_oracle_pair)
@@ -76,7 +104,7 @@ def _worker(rank, world, port, q):
         views_ok = all(p.grad.data_ptr() >= flat.data_ptr() for p in net.parameters())
         average_gradients(flat, world)
         q.put((rank, ok_gather, cd.numpy(), cdm.numpy(), feats.numpy(), cd1.numpy(), cdm1.numpy(), cde.numpy(),
-               (lo, hi), kd.numpy(), ki.numpy(), views_ok, flat.numpy().copy()))
+               (lo, hi), kd.numpy(), ki.numpy(), views_ok, flat.numpy().copy(), cdf.numpy(), cdfm.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -106,8 +134,10 @@ def test_query_sharded_chamfer_and_scan_sharding_world2(oracle):
         net.zero_grad()
         net(scans[r]).square().sum().backward()
         want = want + torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy() / 2
-    for rank, ok_gather, cd, cdm, feats, cd1, cdm1, cde, (lo, hi), kd, ki, views_ok, flat in res:
+    for rank, ok_gather, cd, cdm, feats, cd1, cdm1, cde, (lo, hi), kd, ki, views_ok, flat, cdf, cdfm in res:
         assert views_ok
+        np.testing.assert_allclose(cdf, ref, rtol=1e-6)     # fused: all-gather of payloads, min / sums in one finish step
+        np.testing.assert_allclose(cdfm, refm, rtol=1e-6)
         np.testing.assert_allclose(flat, want, rtol=1e-6, atol=1e-7)   # both ranks hold the average of the two gradients
         np.testing.assert_array_equal(ki, ref_ki[:, lo:hi])   # indices refer to the gathered (rank-ordered) references
         np.testing.assert_array_equal(kd, ref_kd[:, lo:hi])
