@@ -741,6 +741,13 @@ extern "C" int pcst_nn_min_pair_arg_f32(const float* a, const float* b, int B, i
 
 // ---- backward of the Chamfer loss (models/losses.py:24-61 under autograd) ---------------------
 // chamfer[b] = mean_i D(p_i, t_{a(i)}) + mean_j D(t_j, p_{c(j)}),  dD/dp = 2 (p - t), dD/dt = -2 (p - t).
+// D = clamp(raw, min=0) (losses.py:39,56): where the expanded-form distance rounds BELOW zero the clamp is active and
+// autograd passes no gradient; the raw value is re-evaluated here in the forward's own rounding order to decide that.
+__device__ __forceinline__ bool chamfer_pair_clamped(const float* p, const float* t) {
+    const float raw = __fmaf_rn(-2.0f, dot3_chain(p[0], p[1], p[2], t[0], t[1], t[2]),
+                                __fadd_rn(norm3_sq(p[0], p[1], p[2]), norm3_sq(t[0], t[1], t[2])));
+    return raw < 0.0f;
+}
 __global__ void chamfer_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                    const int64_t* __restrict__ arg_pt, const int64_t* __restrict__ arg_tp,
                                    const float* __restrict__ grad_out, int N, int M, float* __restrict__ gp,
@@ -756,6 +763,7 @@ __global__ void chamfer_bwd_kernel(const float* __restrict__ pred, const float* 
         if (e < N) {
             const int i = e;
             const int j = (int)arg_pt[(size_t)b * N + i];
+            if (chamfer_pair_clamped(P + 3 * i, T + 3 * j)) continue;
             const float s = 2.0f * go / (float)N;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -766,6 +774,7 @@ __global__ void chamfer_bwd_kernel(const float* __restrict__ pred, const float* 
         } else {
             const int j = e - N;
             const int i = (int)arg_tp[(size_t)b * M + j];
+            if (chamfer_pair_clamped(P + 3 * i, T + 3 * j)) continue;   // the second direction's matrix is the exact transpose
             const float s = 2.0f * go / (float)M;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {

@@ -201,8 +201,12 @@ class SetAbstraction(nn.Module):
         B, N, _ = xyz.shape
         if start is None:
             start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)  # :36, CPU generator
-        _, new_xyz = ops.fps(xyz, int(self.npoint), start)
-        return new_xyz, query_ball_point(self.radius, self.nsample, xyz, new_xyz)
+        fps_idx, new_xyz = ops.fps(xyz, int(self.npoint), start)
+        if xyz.requires_grad and torch.is_grad_enabled():
+            # the reference's new_xyz = index_points(xyz, fps_idx) (:92) is differentiable w.r.t. xyz: take it from the
+            # differentiable gather instead of the sampling kernel's by-product
+            new_xyz = ops.index_points(xyz, fps_idx)
+        return new_xyz, query_ball_point(self.radius, self.nsample, xyz, new_xyz.detach())
 
     def _mlp_fused(self, xyz, points, new_xyz, group_idx) -> torch.Tensor:
         """Grouping gather + folded MLP + max-pool in one op -> [B,C_out,S] (a channel-first VIEW of the

@@ -456,7 +456,12 @@ class _ChamferLoss(torch.autograd.Function):
             ctx.save_for_backward(pred, target, a1, a2)
         else:          # values only: one sweep serves both directions
             d1, d2 = nn_min_pair(pred, target, 0)
-        return d1.mean(dim=1) + d2.mean(dim=1)
+        out = d1.mean(dim=1) + d2.mean(dim=1)
+        # The kernels' minima drop NaN (FMNMX returns the other operand).  The reference's clamp / min propagate it: a
+        # non-finite coordinate anywhere in a cloud makes every column minimum of that element NaN, hence the loss.  Keep
+        # that signal (a diverging training run must show up as NaN): one fused check per call.
+        finite = torch.isfinite(pred.detach().sum(dim=(1, 2)) + target.detach().sum(dim=(1, 2)))
+        return torch.where(finite, out, torch.full_like(out, float("nan")))
 
     @staticmethod
     def backward(ctx, grad):
@@ -478,6 +483,9 @@ def knn(query: Tensor, ref: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     """query [B,Q,3], ref [B,R,3] -> (dist [B,Q,k] fp64 ascending, idx [B,Q,k] int64); sklearn order."""
     lib = _lib.load()
     _need_cuda(query, ref)
+    if not 1 <= k <= 16:
+        raise ValueError(f"knn: k={k} outside the kernels' range 1..16 (the sorted candidate list lives in registers); "
+                         "the reference's sklearn call accepts any k -- split the query or use k <= 16")
     query, ref = _f32c(query), _f32c(ref)
     B, Q, _ = query.shape
     R = ref.shape[1]

@@ -1071,6 +1071,46 @@ def test_chamfer_backward_matches_autograd_of_reference_formula(api, dev):
     torch.testing.assert_close(gt, t.grad, rtol=1e-4, atol=1e-7)
 
 
+def test_chamfer_backward_honours_the_clamp_and_nan_reaches_the_loss(api, dev):
+    """  Near-coincident clouds: the expanded-form distance of many nearest pairs rounds below zero, the
+    reference's clamp(min=0) is active there and autograd (CPU fp32, the parity target) passes NO gradient for those pairs.
+    And a non-finite coordinate must surface as a NaN loss for that batch element, as clamp / min propagate it."""
+    t_cpu = S.uniform_cloud(3, 2, 600)
+    p_cpu = (t_cpu + 3e-5 * torch.randn(2, 600, 3, generator=torch.Generator().manual_seed(1))).requires_grad_(True)
+    t_ref = t_cpu.clone().requires_grad_(True)
+    psq, tsq = (p_cpu ** 2).sum(-1, keepdim=True), (t_ref ** 2).sum(-1, keepdim=True).transpose(1, 2)
+    raw = psq + tsq + (-2 * torch.bmm(p_cpu, t_ref.transpose(1, 2)))
+    D = torch.clamp(raw, min=0)                                                   # losses.py:36-39 on the CPU
+    (D.min(2)[0].mean(1) + D.min(1)[0].mean(1)).sum().backward()
+    clamped = int((raw.detach().min(2)[0] < 0).sum())
+    assert clamped > 50, clamped                                                  # the case is actually exercised
+    p = p_cpu.detach().to(dev).requires_grad_(True)
+    t = t_cpu.to(dev).requires_grad_(True)
+    api.losses.chamfer_distance_chunked_optimized(p, t).sum().backward()
+    # the unclamped pairs' gradients are ~1e-7; a kernel that ignored the clamp would add 2 (p - t) / N for every clamped pair
+    assert _rel_l2(p.grad.cpu().numpy(), p_cpu.grad.numpy()) < 5e-3
+    assert _rel_l2(t.grad.cpu().numpy(), t_ref.grad.numpy()) < 5e-3
+    bad = S.uniform_cloud(4, 2, 300).to(dev)
+    bad[1, 17, 2] = float("nan")
+    cd = api.losses.chamfer_distance_chunked_optimized(bad, S.uniform_cloud(5, 2, 300).to(dev))
+    assert torch.isfinite(cd[0]) and torch.isnan(cd[1])
+
+
+def test_new_xyz_is_differentiable_with_respect_to_xyz(api, dev):
+    """The reference's new_xyz = index_points(xyz, fps_idx) carries gradient to xyz (models/pointnet2_encoder.py:92)."""
+    sa = api.enc.SetAbstraction(16, 0.4, 8, in_channel=0, mlp=[16, 16, 32]).to(dev).eval()
+    x = S.uniform_cloud(6, 2, 300).to(dev).requires_grad_(True)
+    torch.manual_seed(2)
+    new_xyz, _ = sa(x, None)
+    w = torch.randn(2, 16, 3, generator=torch.Generator().manual_seed(3)).to(dev)
+    (new_xyz * w).sum().backward()
+    torch.manual_seed(2)
+    idx = api.enc.farthest_point_sample(x.detach(), 16)
+    want = torch.zeros_like(x)
+    want.scatter_add_(1, idx[..., None].expand(-1, -1, 3), w)
+    assert torch.equal(x.grad, want)
+
+
 def test_diffusion_loss_call_site(api, dev, oracle):
     L = api.losses.DiffusionLoss(noise_weight=1.0, chamfer_weight=0.1)
     pn, an = torch.randn(2, 300, 3, device=dev), torch.randn(2, 300, 3, device=dev)
