@@ -241,10 +241,10 @@ int pcst_chamfer_bwd_f32(const float* pred, const float* target, const int64_t* 
 
 /* ---- query-sharded Chamfer (multi-GPU): the kernels either side of its single collective ----------------
  * Rank r sweeps its [n_r x M] tile of the pair matrix with pcst_nn_min_pair_f32 (complete row minima of its queries, partial
- * column minima of all M targets).  _pack writes payload [B, P] with P = pcst_chamfer_shard_payload_floats(M) = M + 64:
- * colmin | 32 fp64 partial row sums (float pairs); the ranks all-gather the payloads ([G, B, P]); _finish forms
+ * column minima of all M targets).  _pack writes payload [B, P] with P = pcst_chamfer_shard_payload_floats(M) = M + 256:
+ * colmin | 128 fp64 partial row sums (float pairs); the ranks all-gather the payloads ([G, B, P]); _finish forms
  * out [B] = sum_r rowsum_r / n_total + sum_m min_r colmin_r[m] / M (x 0.5 for form 1, the metric), fp64 sums added in a
- * fixed order: identical on every rank.  ws: B * 32 doubles, 256-byte aligned.
+ * fixed order: identical on every rank.  ws: B * 128 doubles, 256-byte aligned.
  * Replaces all_reduce(MIN) + all_reduce(SUM) + host-side reductions around models/losses.py:61 / evaluation/metrics.py:42. */
 int pcst_chamfer_shard_payload_floats(int M);
 int pcst_chamfer_shard_pack_f32(const float* rowmin, const float* colmin, int B, int n, int M, float* payload,

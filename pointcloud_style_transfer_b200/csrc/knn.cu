@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q, int R, int k,
            int64_t* __restrict__ idx, double* __restrict__ dist, int splits, int tiles_per_split,
            double* __restrict__ part_d, int* __restrict__ part_i, const int* __restrict__ qlist = nullptr,
-           const int* __restrict__ qcount = nullptr) {
+           const int* __restrict__ qcount = nullptr, const int* __restrict__ only_if = nullptr) {
     // reference points of the tile as pairs of consecutive candidates per component, so that one packed
     // FADD2 / FMUL2 / FFMA2 sequence prefilters two candidates against the thread's query
     // (KMAX <= 4) or as float4 rows, one broadcast LDS.128 per candidate (longer lists)
@@ -37,7 +37,9 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q
     float2* ty = tx + kKnnTile / 2;
     float2* tz = ty + kKnnTile / 2;
     const int b = blockIdx.y;
+    if (only_if && !only_if[b]) return;   // (grid search) only the clouds flagged for the plain sweep
     int q = blockIdx.x * kKnnThreads + threadIdx.x;
+    const int slot = q;   // listed mode: position in the list (partial results are stored per slot)
     bool active = q < Q;
     if (qlist) {
         // the queries the grid search handed back (knn_grid.cu): slot -> query index; CTAs past the list leave at once
@@ -141,7 +143,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ ref, int Q
                 idx[((size_t)b * Q + q) * k + t] = j;
                 dist[((size_t)b * Q + q) * k + t] = __dsqrt_rn(v);
             } else {  // squared distances of this slice's k best; merged by knn_merge_kernel
-                const size_t o = (((size_t)b * Q + q) * splits + blockIdx.z) * k + t;
+                const size_t o = (((size_t)b * Q + (qlist ? slot : q)) * splits + blockIdx.z) * k + t;
                 part_d[o] = v;
                 part_i[o] = j;
             }
@@ -184,6 +186,43 @@ __global__ void knn_merge_kernel(const double* __restrict__ part_d, const int* _
     }
 }
 
+// the same merge for LISTED queries: slot s of cloud b (s < qcount[b]) is query qlist[b, s]
+__global__ void knn_merge_listed_kernel(const double* __restrict__ part_d, const int* __restrict__ part_i, int Q, int splits, int k,
+                                        const int* __restrict__ qlist, const int* __restrict__ qcount,
+                                        int64_t* __restrict__ idx, double* __restrict__ dist) {
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= qcount[b]) return;
+    const int q = qlist[(size_t)b * Q + s];
+    double bd[kKnnMaxK];
+    int bi[kKnnMaxK];
+    for (int t = 0; t < k; ++t) {
+        bd[t] = __longlong_as_double(0x7ff0000000000000ll);
+        bi[t] = 0;
+    }
+    const double* pd = part_d + ((size_t)b * Q + s) * splits * k;
+    const int* pi = part_i + ((size_t)b * Q + s) * splits * k;
+    for (int e = 0; e < splits * k; ++e) {
+        double cd = pd[e];
+        int ci = pi[e];
+        if (!(cd < bd[k - 1])) continue;
+        for (int u = 0; u < k; ++u) {
+            if (cd < bd[u]) {
+                const double td = bd[u];
+                const int ti = bi[u];
+                bd[u] = cd;
+                bi[u] = ci;
+                cd = td;
+                ci = ti;
+            }
+        }
+    }
+    for (int t = 0; t < k; ++t) {
+        idx[((size_t)b * Q + q) * k + t] = bi[t];
+        dist[((size_t)b * Q + q) * k + t] = __dsqrt_rn(bd[t]);
+    }
+}
+
 // out[b,q,:] = sum_k w_k feat[b, idx_k, :],  w = 1/(dist + 1e-8), normalised; fp64, rounded once.
 __global__ void knn_interpolate_kernel(const float* __restrict__ feat, const int64_t* __restrict__ idx,
                                        const double* __restrict__ dist, int R, int Q, int k, int C,
@@ -211,34 +250,62 @@ __global__ void knn_interpolate_kernel(const float* __restrict__ feat, const int
     }
 }
 
-size_t knn_grid_workspace_bytes(int B, int Q, int R);
+size_t knn_grid_workspace_bytes(int B, int Q, int R, int k);
 int knn_grid_run(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist, void* ws,
                  cudaStream_t stream);
 
 // brute-force sweep restricted to the queries listed in qlist [B, Q] (first qcount[b] entries of row b): the grid search's
-// fallback for queries it could not finish inside its ring budget
-int knn_sweep_listed(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist,
-                     const int* qlist, const int* qcount, cudaStream_t stream) {
+// fallback for queries it could not finish inside its budget.  The list is usually short (a CTA or two), so the reference
+// range is cut into kListedSplits slices that run as separate CTAs (one CTA sweeping 120k references alone takes a
+// millisecond) and a small kernel merges the per-slice lists.  part_d / part_i: [B, Q, kListedSplits, k] (by list slot).
+// the plain sweep over ALL queries of the clouds whose flag is set (the grid search's verdict "too crowded for a grid")
+int knn_sweep_flagged(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist,
+                      const int* flag, cudaStream_t stream) {
     const int tiles = (R + kKnnTile - 1) / kKnnTile;
     dim3 grid((Q + kKnnThreads - 1) / kKnnThreads, B, 1);
-    if (k <= 1) knn_kernel<1><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
-    else if (k <= 4) knn_kernel<4><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
-    else if (k <= 9) knn_kernel<9><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
-    else knn_kernel<16><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, qlist, qcount);
-    return check_cuda(cudaGetLastError(), "knn_kernel (listed queries)");
+    if (k <= 1) knn_kernel<1><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, nullptr, nullptr, flag);
+    else if (k <= 4) knn_kernel<4><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, nullptr, nullptr, flag);
+    else if (k <= 9) knn_kernel<9><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, nullptr, nullptr, flag);
+    else knn_kernel<16><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, 1, tiles, nullptr, nullptr, nullptr, nullptr, flag);
+    return check_cuda(cudaGetLastError(), "knn_kernel (flagged clouds)");
 }
 
-// The exact grid search (knn_grid.cu) is the default for large SELF queries (uniformity_score's 9-NN of a cloud against
-// itself, evaluation/metrics.py:152-153: every query sits on a reference, so the ring walk ends at once; measured 2.8 ms
-// against 9.6 ms for the sweep at 120k points).  Between two different clouds its gain depends on how evenly the references
-// fill their box: 1.00 against 1.35 ms for the 90k x 30k interpolation of a LiDAR scan, no gain between two different
-// scans, and a loss on the Gaussian noise clouds of the early sampling steps (a uniform cell edge cannot serve a 200:1
-// density contrast; profiles/r02/knn_grid.md), so the sweep stays the default there.  knn.grid = 1 / 2 forces it on / off.
+constexpr int kListedSplits = 16;
+size_t knn_listed_part_bytes(int B, int Q, int k) {
+    return align_up((size_t)B * Q * kListedSplits * k * sizeof(double), 256) + align_up((size_t)B * Q * kListedSplits * k * sizeof(int), 256);
+}
+int knn_sweep_listed(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist,
+                     const int* qlist, const int* qcount, void* part, cudaStream_t stream) {
+    const int tiles = (R + kKnnTile - 1) / kKnnTile;
+    int splits = tiles < kListedSplits ? tiles : kListedSplits;
+    const int tps = (tiles + splits - 1) / splits;
+    splits = (tiles + tps - 1) / tps;
+    while (splits > 1 && (R - (splits - 1) * tps * kKnnTile) < k) splits = 1;   // every slice must hold at least k points
+    double* part_d = (double*)part;
+    int* part_i = (int*)((char*)part + align_up((size_t)B * Q * kListedSplits * k * sizeof(double), 256));
+    const int tps_arg = splits > 1 ? tps : tiles;
+    dim3 grid((Q + kKnnThreads - 1) / kKnnThreads, B, splits);
+    if (k <= 1) knn_kernel<1><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i, qlist, qcount);
+    else if (k <= 4) knn_kernel<4><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i, qlist, qcount);
+    else if (k <= 9) knn_kernel<9><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i, qlist, qcount);
+    else knn_kernel<16><<<grid, kKnnThreads, 0, stream>>>(query, ref, Q, R, k, idx, dist, splits, tps_arg, part_d, part_i, qlist, qcount);
+    PCST_CUDA(cudaGetLastError());
+    if (splits > 1) {
+        knn_merge_listed_kernel<<<dim3((Q + 127) / 128, B), 128, 0, stream>>>(part_d, part_i, Q, splits, k, qlist, qcount, idx, dist);
+        PCST_CUDA(cudaGetLastError());
+    }
+    return PCST_OK;
+}
+
+// The exact grid search (knn_grid.cu) takes over when both clouds are large: it beats the sweep on every cloud pair measured
+// (profiles/r02/knn_grid.md): 3-NN 90k x 30k 1.36 -> 0.75 ms, 9-NN self query 120k 9.41 -> 1.04 ms, 120k x 120k between two
+// scans 6.1 -> 3.3 ms, Gaussian noise clouds 1.51 -> 1.08 ms.  knn.grid = 1 / 2 forces it on / off.
 static bool knn_use_grid(int Q, int R, bool self_query = false) {
+    (void)self_query;
     const int t = tuning("knn.grid", 0);
     if (t == 1) return true;
     if (t == 2) return false;
-    return self_query && R >= 16384;
+    return R >= 16384 && Q >= 16384;
 }
 
 }  // namespace pcst
@@ -258,7 +325,7 @@ static int knn_splits(int B, int Q, int R) {
 extern "C" size_t pcst_knn_workspace_bytes(int B, int Q, int R, int k) {
     if (B <= 0 || Q <= 0 || R <= 0 || k <= 0) return 0;
     // (a caller cannot say here whether query == ref: size for the grid whenever a self query of this shape would take it)
-    if (knn_use_grid(Q, R, Q == R)) return knn_grid_workspace_bytes(B, Q, R);
+    if (knn_use_grid(Q, R, Q == R)) return knn_grid_workspace_bytes(B, Q, R, k);
     const int s = knn_splits(B, Q, R);
     if (s == 1) return 0;
     return align_up((size_t)B * Q * s * k * sizeof(double), 256) + align_up((size_t)B * Q * s * k * sizeof(int), 256);
@@ -266,7 +333,7 @@ extern "C" size_t pcst_knn_workspace_bytes(int B, int Q, int R, int k) {
 
 extern "C" int pcst_knn_kernel_launches(int B, int Q, int R, int k, int self_query) {
     if (B <= 0 || Q <= 0 || R <= 0 || k <= 0) return 0;
-    if (knn_use_grid(Q, R, self_query && Q == R)) return 10;  // bounding box, parameters, count, refine, count, scan, scatter, ring walk, listed sweep (+ memsets)
+    if (knn_use_grid(Q, R, self_query && Q == R)) return 16;  // bounding box, parameters, count, refine, count, scan, scatter, ring walk, listed sweep (+ memsets)
     return knn_splits(B, Q, R) > 1 ? 2 : 1;
 }
 
@@ -278,7 +345,7 @@ extern "C" int pcst_knn_f32(const float* query, const float* ref, int B, int Q, 
     PCST_CHECK_ARG(B <= 65535, "B must be <= 65535");
     PCST_CHECK_ARG(k >= 1 && k <= kKnnMaxK && k <= R, "k must be in [1, min(16, R)]");
     if (knn_use_grid(Q, R, query == ref && Q == R)) {
-        const size_t need_g = knn_grid_workspace_bytes(B, Q, R);
+        const size_t need_g = knn_grid_workspace_bytes(B, Q, R, k);
         if (!ws || ws_bytes < need_g || ((uintptr_t)ws & 255)) {
             set_error("pcst_knn_f32: workspace too small or misaligned (%zu < %zu)", ws_bytes, need_g);
             return PCST_ERR_WORKSPACE;

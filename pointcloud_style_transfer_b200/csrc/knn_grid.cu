@@ -18,9 +18,12 @@
 // real pass; (b) the references are binned at THREE cell edges (h, 4h, 16h: one counting sort each, built by the same three
 // launches): a query that is not finished after kGridMaxRing rings at one level restarts at the next coarser one, so a
 // point in a sparse region pays 125 look-ups per level instead of a walk over thousands of empty fine cells; (c) a query
-// that no level finishes, or that has spent kGridBudget pair evaluations (a lone thread walking big coarse cells is slower
-// than the tiled sweep), is appended to a list, and the listed queries are answered by the tiled brute-force sweep of
-// knn.cu afterwards -- exactness never depends on the grid.
+// that no level finishes, or whose next cell would take it past max(2048, R / 16) pair evaluations (the kernel ends with its
+// slowest thread, and a lone thread ranking a coarse cell's thousands of references takes milliseconds), is appended to a
+// list, and the listed queries are answered afterwards by the tiled brute-force sweep of knn.cu, cut into 16 reference slices
+// so that a short list still spreads over the machine -- exactness never depends on the grid.
+// Measured (tools/knn_grid_ab.py, ms, grid / sweep): LiDAR 90k x 30k 3-NN 0.75 / 1.36; 120k self 9-NN 1.04 / 9.41; 120k x
+// 120k between two scans 3.30 / 6.08; Gaussian noise cloud 120k x 30k 1.08 / 1.51; half-noised scan 0.90 / 1.51.
 // Bound: latency / L2 gather; tens of pair evaluations and 27-343 cell look-ups per query instead of R.
 #include "common.cuh"
 
@@ -29,9 +32,9 @@ namespace pcst {
 constexpr int kGridLevels = 3;       // cell edge h, 4h, 16h
 constexpr int kGridMaxRing = 2;      // rings per level: (2 * 2 + 1)^3 = 125 cells, then the next (coarser) level
 constexpr float kGridTargetOcc = 2.0f;  // references per occupied cell the refinement aims at
-constexpr int kGridBudget = 1 << 30; // pair evaluations a query may spend in the grid before it is handed to the tiled sweep
-                                     // (off: with 1536 so many queries of a LiDAR scan overflow -- its near field packs
-                                     // hundreds of points into a cell -- that the listed sweep costs more than it saves)
+constexpr int kGridBudget = 2048;    // pair evaluations (at least; R / 16 for large clouds) a query may spend in the grid before it is handed to the tiled sweep:
+                                     // the kernel ends with its SLOWEST thread, and a lone thread ranking the thousands of
+                                     // references of coarse cells (a query in the far tail of a noise cloud) takes milliseconds
 constexpr int kGridMaxDim = 1024;    // cells per axis
 
 struct GridParams {
@@ -141,21 +144,50 @@ __global__ void grid_count_kernel(const float* __restrict__ ref, int R, const Gr
     }
 }
 
-// exclusive scan of one cloud's cell counts at one level: one CTA of 1024 threads, each owning a contiguous run of cells
+// Exclusive scan of every (cloud, level)'s cell counts, coalesced and spread over the machine (a level-0 grid has up to
+// 24 R cells; a single CTA walking them took 1.9 ms per call, more than the search itself): blocks of kScanBlock cells
+//   1. block sums   2. exclusive scan of the block sums (one CTA per (cloud, level))   3. in-block scan + block offset.
+constexpr int kScanBlock = 2048;    // cells per CTA in passes 1 and 3 (256 threads x 8)
+
+__device__ __forceinline__ int block_reduce_i32(int v, int* sm) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int tot = 0;
+    if (threadIdx.x < 32) {
+        tot = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+    }
+    return tot;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256)
+grid_scan_sums_kernel(const GridParams* __restrict__ gp, GridArrays ga, int* __restrict__ bsum, int maxblocks) {
+    __shared__ int sm[8];
+    const int b = blockIdx.y, l = blockIdx.z;
+    const int n = gp[(size_t)b * kGridLevels + l].ncell;
+    const int base = blockIdx.x * kScanBlock;
+    if (base >= n) return;
+    const int* c = ga.counts[l] + (size_t)b * ga.cap[l];
+    int v = 0;
+    for (int i = base + threadIdx.x; i < min(n, base + kScanBlock); i += 256) v += c[i];
+    const int tot = block_reduce_i32(v, sm);
+    if (threadIdx.x == 0) bsum[((size_t)b * kGridLevels + l) * maxblocks + blockIdx.x] = tot;
+}
+
 __global__ void __launch_bounds__(1024)
-grid_scan_kernel(const GridParams* __restrict__ gp, GridArrays ga) {
+grid_scan_blocks_kernel(const GridParams* __restrict__ gp, int* __restrict__ bsum, int maxblocks) {
     __shared__ int part[1024];
     const int b = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
-    const int n = gp[(size_t)b * kGridLevels + l].ncell;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, t * per), hi = min(n, lo + per);
-    const int* c = ga.counts[l] + (size_t)b * ga.cap[l];
-    int* s = ga.starts[l] + (size_t)b * ga.cap[l];
+    const int nb = (gp[(size_t)b * kGridLevels + l].ncell + kScanBlock - 1) / kScanBlock;
+    int* s = bsum + ((size_t)b * kGridLevels + l) * maxblocks;
+    const int per = (nb + 1023) / 1024;
+    const int lo = min(nb, t * per), hi = min(nb, lo + per);
     int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += c[i];
+    for (int i = lo; i < hi; ++i) sum += s[i];
     part[t] = sum;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+    for (int off = 1; off < 1024; off <<= 1) {
         const int v = t >= off ? part[t - off] : 0;
         __syncthreads();
         part[t] += v;
@@ -163,8 +195,44 @@ grid_scan_kernel(const GridParams* __restrict__ gp, GridArrays ga) {
     }
     int run = part[t] - sum;
     for (int i = lo; i < hi; ++i) {
+        const int c = s[i];
         s[i] = run;
-        run += c[i];
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grid_scan_apply_kernel(const GridParams* __restrict__ gp, GridArrays ga, const int* __restrict__ bsum, int maxblocks) {
+    __shared__ int warp_tot[8];
+    const int b = blockIdx.y, l = blockIdx.z;
+    const int n = gp[(size_t)b * kGridLevels + l].ncell;
+    const int base = blockIdx.x * kScanBlock;
+    if (base >= n) return;
+    const int* c = ga.counts[l] + (size_t)b * ga.cap[l];
+    int* s = ga.starts[l] + (size_t)b * ga.cap[l];
+    // thread t owns the 8 consecutive cells base + 8 t ..: coalesced 32-byte loads, in-thread scan, warp scan, block scan
+    const int i0 = base + threadIdx.x * 8;
+    int v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = i0 + j < n ? c[i0 + j] : 0;
+        sum += v[j];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    int run = bsum[((size_t)b * kGridLevels + l) * maxblocks + blockIdx.x] + woff + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (i0 + j < n) s[i0 + j] = run;
+        run += v[j];
     }
 }
 
@@ -182,13 +250,52 @@ __global__ void grid_scatter_kernel(const float* __restrict__ ref, int R, const 
     }
 }
 
+// Crowding check, on the device: for every 8th reference, how many references lie in the 27 finest-level cells around it
+// (= what a query sitting there evaluates at least).  Clouds whose points pile up (the tanh-saturated faces of the sampling
+// loop's intermediate clouds, dense clusters) would send most queries over the evaluation budget and pay the grid AND the
+// sweep; when the mean exceeds kGridCrowded the whole cloud goes to the sweep instead.
+constexpr int kGridCrowded = 1500;
+struct GridVerdict {
+    unsigned long long sum;
+    int n, pad;
+};
+__global__ void grid_crowding_kernel(const float* __restrict__ ref, int R, const GridParams* __restrict__ gp, GridArrays ga,
+                                     GridVerdict* __restrict__ vd) {
+    const int b = blockIdx.y;
+    const GridParams p = gp[(size_t)b * kGridLevels];
+    const int* ct = ga.counts[0] + (size_t)b * ga.cap[0];
+    unsigned long long local = 0;
+    int cnt = 0;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8; j < R; j += gridDim.x * blockDim.x * 8) {
+        const float* q = ref + ((size_t)b * R + j) * 3;
+        const int cx = grid_axis(q[0], p.minx, p.inv_h, p.nx, nullptr), cy = grid_axis(q[1], p.miny, p.inv_h, p.ny, nullptr),
+                  cz = grid_axis(q[2], p.minz, p.inv_h, p.nz, nullptr);
+        int s = 0;
+        for (int z = max(0, cz - 1); z <= min(p.nz - 1, cz + 1); ++z)
+            for (int y = max(0, cy - 1); y <= min(p.ny - 1, cy + 1); ++y)
+                for (int x = max(0, cx - 1); x <= min(p.nx - 1, cx + 1); ++x) s += __ldg(ct + ((size_t)z * p.ny + y) * p.nx + x);
+        local += (unsigned long long)s;
+        ++cnt;
+    }
+    if (cnt) {
+        atomicAdd(&vd[b].sum, local);
+        atomicAdd(&vd[b].n, cnt);
+    }
+}
+
+__global__ void grid_verdict_kernel(const GridVerdict* __restrict__ vd, int B, int force, int* __restrict__ crowded) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) crowded[b] = !force && vd[b].sum > (unsigned long long)kGridCrowded * (unsigned long long)max(vd[b].n, 1);
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(128)
 grid_query_kernel(const float* __restrict__ query, int Q, int R, int k, const GridParams* __restrict__ gp, GridArrays ga,
-                  int64_t* __restrict__ idx, double* __restrict__ dist, int* __restrict__ qlist, int* __restrict__ qcount) {
+                  int64_t* __restrict__ idx, double* __restrict__ dist, int* __restrict__ qlist, int* __restrict__ qcount,
+                  const int* __restrict__ crowded) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
+    if (q >= Q || crowded[b]) return;   // a crowded cloud is answered by the plain sweep (knn_sweep_flagged)
     const float* qp = query + ((size_t)b * Q + q) * 3;
     const float fx = qp[0], fy = qp[1], fz = qp[2];
     const double qx = fx, qy = fy, qz = fz;
@@ -231,7 +338,8 @@ grid_query_kernel(const float* __restrict__ query, int Q, int R, int k, const Gr
 
     bool done = false;
     int spent = 0;  // pair evaluations so far: a thread walking big coarse cells alone is slower than the tiled sweep
-    for (int l = 0; l < kGridLevels && !done && spent <= kGridBudget; ++l) {
+    const int budget = max(kGridBudget, R / 16);
+    for (int l = 0; l < kGridLevels && !done && spent <= budget; ++l) {
         const GridParams p = gp[(size_t)b * kGridLevels + l];
         const int* st = ga.starts[l] + (size_t)b * ga.cap[l];
         const int* ct = ga.counts[l] + (size_t)b * ga.cap[l];
@@ -245,7 +353,11 @@ grid_query_kernel(const float* __restrict__ query, int Q, int R, int k, const Gr
         auto scan_cell = [&](int x, int y, int z) {
             const size_t cell = ((size_t)z * p.ny + y) * p.nx + x;
             const int n = __ldg(ct + cell);
-            if (n == 0 || spent > kGridBudget) return;
+            if (n == 0 || spent > budget) return;
+            if (spent + n > budget) {   // this cell alone would blow the budget: stop here, the sweep takes the query
+                spent = budget + 1;
+                return;
+            }
             spent += n;
             const float4* c = pts + __ldg(st + cell);
             for (int t = 0; t < n; ++t) consider(__ldg(c + t));
@@ -275,7 +387,7 @@ grid_query_kernel(const float* __restrict__ query, int Q, int R, int k, const Gr
             // every reference outside the visited cube is farther than (r + w) cells; 4e-3 of a cell covers the fp32
             // rounding of the cell coordinates of the query and of the references (|scaled coordinate| <= 1024)
             const double reach = (double)fmaxf((float)r + w - 4e-3f, 0.f) * (double)p.h;
-            if (spent > kGridBudget) break;             // over budget: cells may have been left out, the list is not final
+            if (spent > budget) break;                  // over budget: cells may have been left out, the list is not final
             if (kth() <= reach * reach || r == rmax) {  // r == rmax: the whole grid has been visited
                 done = true;
                 break;
@@ -300,11 +412,14 @@ grid_query_kernel(const float* __restrict__ query, int Q, int R, int k, const Gr
 
 // workspace: box | probe params | level params | nocc | qcount | per level (counts, fill, starts) | per level sorted | qlist
 struct GridWs {
-    size_t box, probe, params, nocc, qcount, cells, cells_end, sorted[kGridLevels], qlist, total;
+    size_t box, probe, params, nocc, qcount, verdict, crowded, cells, cells_end, sorted[kGridLevels], qlist, bsum, part, total;
+    int maxblocks;
     size_t counts[kGridLevels], fill[kGridLevels], starts[kGridLevels];
     int cap0, cap[kGridLevels];
 };
-static GridWs grid_ws(int B, int Q, int R) {
+size_t knn_listed_part_bytes(int B, int Q, int k);
+
+static GridWs grid_ws(int B, int Q, int R, int k = 16) {
     GridWs w;
     w.cap0 = 24 * R + 64;
     size_t off = 0;
@@ -314,6 +429,8 @@ static GridWs grid_ws(int B, int Q, int R) {
     w.params = take((size_t)B * kGridLevels * sizeof(GridParams));
     w.nocc = take((size_t)B * sizeof(int));
     w.qcount = take((size_t)B * sizeof(int));
+    w.verdict = take((size_t)B * sizeof(GridVerdict));
+    w.crowded = take((size_t)B * sizeof(int));
     w.cells = off;
     for (int l = 0; l < kGridLevels; ++l) {
         w.cap[l] = (w.cap0 >> (2 * l)) + 64;
@@ -324,18 +441,23 @@ static GridWs grid_ws(int B, int Q, int R) {
     for (int l = 0; l < kGridLevels; ++l) w.starts[l] = take((size_t)B * w.cap[l] * sizeof(int));
     for (int l = 0; l < kGridLevels; ++l) w.sorted[l] = take((size_t)B * R * sizeof(float4));
     w.qlist = take((size_t)B * Q * sizeof(int));
+    w.maxblocks = (w.cap0 + 64 + kScanBlock - 1) / kScanBlock;
+    w.bsum = take((size_t)B * kGridLevels * w.maxblocks * sizeof(int));
+    w.part = take(knn_listed_part_bytes(B, Q, k));
     w.total = off;
     return w;
 }
 
-size_t knn_grid_workspace_bytes(int B, int Q, int R) { return grid_ws(B, Q, R).total; }
+size_t knn_grid_workspace_bytes(int B, int Q, int R, int k) { return grid_ws(B, Q, R, k).total; }
 
 int knn_sweep_listed(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist,
-                     const int* qlist, const int* qcount, cudaStream_t stream);
+                     const int* qlist, const int* qcount, void* part, cudaStream_t stream);
+int knn_sweep_flagged(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist,
+                      const int* flag, cudaStream_t stream);
 
 int knn_grid_run(const float* query, const float* ref, int B, int Q, int R, int k, int64_t* idx, double* dist, void* ws,
                  cudaStream_t stream) {
-    const GridWs w = grid_ws(B, Q, R);
+    const GridWs w = grid_ws(B, Q, R, k);
     char* base = (char*)ws;
     float* box = (float*)(base + w.box);
     GridParams* probe = (GridParams*)(base + w.probe);
@@ -354,7 +476,9 @@ int knn_grid_run(const float* query, const float* ref, int B, int Q, int R, int 
     int st = pcst_minmax_f32(ref, B, R, box, (pcst_stream_t)stream);
     if (st != PCST_OK) return st;
     // probing pass at h0 = cbrt(volume / R) (at most 2R + 64 cells, counted in level 0's array)
-    PCST_CUDA(cudaMemsetAsync(nocc, 0, w.cells - w.nocc, stream));                                // nocc and qcount
+    PCST_CUDA(cudaMemsetAsync(nocc, 0, w.cells - w.nocc, stream));                                // nocc, qcount and verdict
+    GridVerdict* vd = (GridVerdict*)(base + w.verdict);
+    int* crowded = (int*)(base + w.crowded);
     PCST_CUDA(cudaMemsetAsync(ga.counts[0], 0, (size_t)B * w.cap[0] * sizeof(int), stream));
     grid_params_kernel<<<(B + 63) / 64, 64, 0, stream>>>(box, B, R, 2 * R + 64, probe);
     PCST_CUDA(cudaGetLastError());
@@ -368,17 +492,29 @@ int knn_grid_run(const float* query, const float* ref, int B, int Q, int R, int 
     PCST_CUDA(cudaMemsetAsync(base + w.cells, 0, w.cells_end - w.cells, stream));                 // counts and fill of every level
     grid_count_kernel<<<dim3(blocks, B), 256, 0, stream>>>(ref, R, gp, ga);
     PCST_CUDA(cudaGetLastError());
-    grid_scan_kernel<<<dim3(B, kGridLevels), 1024, 0, stream>>>(gp, ga);
+    int* bsum = (int*)(base + w.bsum);
+    grid_scan_sums_kernel<<<dim3(w.maxblocks, B, kGridLevels), 256, 0, stream>>>(gp, ga, bsum, w.maxblocks);
+    PCST_CUDA(cudaGetLastError());
+    grid_scan_blocks_kernel<<<dim3(B, kGridLevels), 1024, 0, stream>>>(gp, bsum, w.maxblocks);
+    PCST_CUDA(cudaGetLastError());
+    grid_scan_apply_kernel<<<dim3(w.maxblocks, B, kGridLevels), 256, 0, stream>>>(gp, ga, bsum, w.maxblocks);
     PCST_CUDA(cudaGetLastError());
     grid_scatter_kernel<<<dim3(blocks, B), 256, 0, stream>>>(ref, R, gp, ga);
     PCST_CUDA(cudaGetLastError());
-    dim3 grid((Q + 127) / 128, B);
-    if (k <= 1) grid_query_kernel<1><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
-    else if (k <= 4) grid_query_kernel<4><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
-    else if (k <= 9) grid_query_kernel<9><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
-    else grid_query_kernel<16><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount);
+    const int force = tuning("knn.grid", 0) == 1;   // forced on: no crowding verdict (tests of the walk itself)
+    grid_crowding_kernel<<<dim3(min(blocks, (R / 8 + 255) / 256 + 1), B), 256, 0, stream>>>(ref, R, gp, ga, vd);
     PCST_CUDA(cudaGetLastError());
-    return knn_sweep_listed(query, ref, B, Q, R, k, idx, dist, qlist, qcount, stream);
+    grid_verdict_kernel<<<(B + 63) / 64, 64, 0, stream>>>(vd, B, force, crowded);
+    PCST_CUDA(cudaGetLastError());
+    dim3 grid((Q + 127) / 128, B);
+    if (k <= 1) grid_query_kernel<1><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount, crowded);
+    else if (k <= 4) grid_query_kernel<4><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount, crowded);
+    else if (k <= 9) grid_query_kernel<9><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount, crowded);
+    else grid_query_kernel<16><<<grid, 128, 0, stream>>>(query, Q, R, k, gp, ga, idx, dist, qlist, qcount, crowded);
+    PCST_CUDA(cudaGetLastError());
+    st = knn_sweep_flagged(query, ref, B, Q, R, k, idx, dist, crowded, stream);
+    if (st != PCST_OK) return st;
+    return knn_sweep_listed(query, ref, B, Q, R, k, idx, dist, qlist, qcount, base + w.part, stream);
 }
 
 }  // namespace pcst

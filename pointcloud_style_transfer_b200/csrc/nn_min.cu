@@ -810,7 +810,7 @@ extern "C" int pcst_chamfer_bwd_f32(const float* pred, const float* target, cons
 // and added in a fixed order, so every rank gets the same bits.
 namespace pcst {
 
-constexpr int kShardParts = 32;   // CTAs per batch element in pack / finish = fp64 partial sums per rank and element
+constexpr int kShardParts = 128;  // CTAs per batch element in pack / finish = fp64 partial sums per rank and element
 constexpr int kShardThreads = 256;
 
 __device__ __forceinline__ double block_sum_f64(double s, double* part) {
@@ -861,24 +861,35 @@ chamfer_shard_colmin_kernel(const float* __restrict__ gathered, int G, int B, in
     if (t == 0) colpart[(size_t)b * kShardParts + c] = tot;
 }
 
-// stage 2: one warp per element adds the column partials and the G x kShardParts row partials in a fixed order
-__global__ void chamfer_shard_finish_kernel(const float* __restrict__ gathered, const double* __restrict__ colpart, int G, int B,
-                                            int M, double n_total, int form, float* __restrict__ out) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// stage 2: one CTA of kShardParts threads per element: thread c adds column partial c and the G row partials of slot c,
+// then a fixed-shape tree over the slots (deterministic: every rank performs the same additions in the same order)
+__global__ void __launch_bounds__(kShardParts)
+chamfer_shard_finish_kernel(const float* __restrict__ gathered, const double* __restrict__ colpart, int G, int B, int M,
+                            double n_total, int form, float* __restrict__ out) {
+    __shared__ double cs[kShardParts], rs[kShardParts];
+    const int b = blockIdx.x, c = threadIdx.x;
     const size_t stride = (size_t)B * (M + 2 * kShardParts);
-    double cols = 0.0, rows = 0.0;
-    for (int c = 0; c < kShardParts; ++c) cols += colpart[(size_t)b * kShardParts + c];
+    double rows = 0.0;
     for (int g = 0; g < G; ++g) {
-        const float* p = gathered + (size_t)g * stride + (size_t)b * (M + 2 * kShardParts) + M;
-        for (int c = 0; c < kShardParts; ++c) {
-            const unsigned long long bits = (unsigned long long)__float_as_uint(p[2 * c]) | ((unsigned long long)__float_as_uint(p[2 * c + 1]) << 32);
-            rows += __longlong_as_double((long long)bits);
-        }
+        const float* p = gathered + (size_t)g * stride + (size_t)b * (M + 2 * kShardParts) + M + 2 * c;
+        const unsigned long long bits = (unsigned long long)__float_as_uint(p[0]) | ((unsigned long long)__float_as_uint(p[1]) << 32);
+        rows += __longlong_as_double((long long)bits);
     }
-    double v = rows / n_total + cols / (double)M;
-    if (form != 0) v *= 0.5;
-    out[b] = (float)v;
+    cs[c] = colpart[(size_t)b * kShardParts + c];
+    rs[c] = rows;
+    __syncthreads();
+    for (int o = kShardParts / 2; o > 0; o >>= 1) {
+        if (c < o) {
+            cs[c] += cs[c + o];
+            rs[c] += rs[c + o];
+        }
+        __syncthreads();
+    }
+    if (c == 0) {
+        double v = rs[0] / n_total + cs[0] / (double)M;
+        if (form != 0) v *= 0.5;
+        out[b] = (float)v;
+    }
 }
 
 }  // namespace pcst
@@ -900,11 +911,11 @@ extern "C" int pcst_chamfer_shard_finish_f32(const float* gathered, int G, int B
     PCST_CHECK_ARG(gathered && out && ws, "null pointer");
     PCST_CHECK_ARG(G > 0 && B > 0 && B <= 65535 && M > 0 && n_total > 0, "bad sizes");
     if (ws_bytes < (size_t)B * kShardParts * sizeof(double) || ((uintptr_t)ws & 255)) {
-        set_error("pcst_chamfer_shard_finish_f32: workspace too small or misaligned (needs B * 32 doubles)");
+        set_error("pcst_chamfer_shard_finish_f32: workspace too small or misaligned (needs B * 128 doubles)");
         return PCST_ERR_WORKSPACE;
     }
     chamfer_shard_colmin_kernel<<<dim3(kShardParts, B), kShardThreads, 0, stream>>>(gathered, G, B, M, (double*)ws);
     PCST_CUDA(cudaGetLastError());
-    chamfer_shard_finish_kernel<<<(B + 63) / 64, 64, 0, stream>>>(gathered, (const double*)ws, G, B, M, (double)n_total, form, out);
+    chamfer_shard_finish_kernel<<<B, kShardParts, 0, stream>>>(gathered, (const double*)ws, G, B, M, (double)n_total, form, out);
     return check_cuda(cudaGetLastError(), "chamfer_shard_finish_kernel");
 }

@@ -773,8 +773,8 @@ KERNELS_PER_CALL["pcst_chamfer_shard_finish_f32"] = 1
 
 
 def chamfer_shard_pack(rowmin: Tensor, colmin: Tensor) -> Tensor:
-    """rowmin [B,n] (this rank's complete row minima), colmin [B,M] (partial column minima) -> payload [B, M + 64] fp32 =
-    colmin | 32 fp64 partial row sums as float pairs: what the ranks all-gather."""
+    """rowmin [B,n] (this rank's complete row minima), colmin [B,M] (partial column minima) -> payload [B, M + 256] fp32 =
+    colmin | 128 fp64 partial row sums as float pairs: what the ranks all-gather."""
     lib = _lib.load()
     _need_cuda(rowmin, colmin)
     rowmin, colmin = _f32c(rowmin), _f32c(colmin)
@@ -787,7 +787,7 @@ def chamfer_shard_pack(rowmin: Tensor, colmin: Tensor) -> Tensor:
 
 
 def chamfer_shard_finish(gathered: Tensor, n_total: int, form: int) -> Tensor:
-    """gathered [G, B, M + 64] (the all-gathered payloads) -> chamfer [B] fp32 (identical on every rank)."""
+    """gathered [G, B, M + 256] (the all-gathered payloads) -> chamfer [B] fp32 (identical on every rank)."""
     lib = _lib.load()
     _need_cuda(gathered)
     gathered = _f32c(gathered)
@@ -795,7 +795,7 @@ def chamfer_shard_finish(gathered: Tensor, n_total: int, form: int) -> Tensor:
     M = P - (lib.pcst_chamfer_shard_payload_floats(1) - 1)
     out = torch.empty(B, dtype=torch.float32, device=gathered.device)
     with torch.cuda.device(gathered.device):
-        ws = _workspace(B * 32 * 8, gathered.device)
+        ws = _workspace(B * 128 * 8, gathered.device)
         _call("pcst_chamfer_shard_finish_f32", _p(gathered), G, B, M, int(n_total), int(form), _p(out), _p(ws), ws.numel(),
               _stream(), kernels=2)
     return out

@@ -37,7 +37,7 @@ def _oracle_knn(q, r, k):
     return torch.from_numpy(d), torch.from_numpy(i)
 
 
-_PARTS = 32  # fp64 partial row sums per payload row (pcst_chamfer_shard_payload_floats(M) - M = 64 float slots)
+_PARTS = 128  # fp64 partial row sums per payload row (pcst_chamfer_shard_payload_floats(M) - M = 256 float slots)
 
 
 def _cpu_pack(rowmin, colmin):

@@ -1,0 +1,46 @@
+"""Round 2: one launch of every hot kernel added or changed in this round (the command `ncu --set full` wraps):
+FPS (default and look-ahead), tcgen05 train-mode GEMMs / wgrad at the config-4 per-GPU shape, the fused denoiser, the
+grid kNN, the sharded-Chamfer pack / finish kernels, plus the eval-mode MLP at the batched shape."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pointcloud_style_transfer_b200 import _lib, ops, synthetic as S  # noqa: E402
+from pointcloud_style_transfer_b200.config import Config  # noqa: E402
+from pointcloud_style_transfer_b200.models import diffusion_model as DM  # noqa: E402
+from pointcloud_style_transfer_b200.models.pointnet2_encoder import PointNet2Encoder  # noqa: E402
+
+dev = torch.device("cuda:0")
+x = S.lidar_scan(0).to(dev)
+y = S.lidar_scan(100).to(dev)
+start = torch.tensor([1234], device=dev)
+torch.manual_seed(42)
+enc_eval = PointNet2Encoder(feature_dim=256, mlp_precision=1).eval().to(dev)
+enc_train = PointNet2Encoder(feature_dim=256, mlp_precision=1).train().to(dev)
+xb = torch.cat([S.lidar_scan(i, 4096) for i in range(4)], 0).to(dev)          # config 4 per GPU after the downsample
+x16 = torch.cat([S.lidar_scan(i, 16384) for i in range(8)], 0).to(dev)
+net = DM.NoisePredictor(Config()).to(dev).eval()
+xc, tt, st = torch.randn(2, 30000, 3, device=dev), torch.tensor([500, 500], device=dev), torch.randn(2, 256, device=dev)
+
+for rep in range(2):
+    with torch.no_grad():
+        ops.fps(x, 512, start)
+        _lib.set_tuning("fps.lookahead", 1)
+        ops.fps(x, 512, start)
+        _lib.set_tuning("fps.lookahead", 0)
+        torch.manual_seed(1)
+        enc_eval(x)
+        torch.manual_seed(1)
+        enc_eval(x16)                                   # batched eval-mode MLP (8 x 16384)
+        net(xc, tt, st)                                 # fused denoiser
+        ops.knn(x, x, 9)                                # grid search (self query)
+        rowmin, colmin = ops.nn_min_pair(x[:, :15000].contiguous(), y, 0)
+        ops.chamfer_shard_finish(torch.stack([ops.chamfer_shard_pack(rowmin, colmin)] * 8), 120000, 0)
+    torch.manual_seed(1)
+    f = enc_train(xb)                                   # train-mode forward: tcgen05 GEMMs + statistics + pooling
+    f.square().sum().backward()                         # dgrad / wgrad / BatchNorm backward
+    enc_train.zero_grad()
+    torch.cuda.synchronize()
+print("ncu_once_r2 ok")
