@@ -16,7 +16,11 @@
 //   * the hidden 2F activations are produced and consumed in two halves of F columns (TMEM columns [256, 256 + F)), so
 //     the widest operand in shared memory is 128 x 256 bf16;
 //   * weights are packed once (bf16 [K/8][N][8] blocks in step order) and streamed through a 4-stage TMA ring; they stay
-//     L2-resident (3.3 MB for F = 256).
+//     L2-resident (3.3 MB for F = 256).  Every 128-row tile needs ALL of them (3.3 MB per tile, 64 bytes per SM and clock at
+//     the tensor floor -- more than the L2 delivers to 148 SMs at once), so the kernel can run as thread-block clusters of 2 or 4 CTAs
+//     that walk their tiles in lockstep and share every stage: each CTA fetches 1/C of it and MULTICASTS it into all
+//     shared memories (cp.async.bulk ... .multicast::cluster), and a stage is refilled once all MMA issuers have
+//     committed it (tcgen05.commit.multicast::cluster onto every CTA's empty barrier).  Tuning key noise.cluster.
 // Warp roles as in sa_mlp_tc.cu: warps 0-3 = operand build + epilogues (thread = row = TMEM lane), warp 4 = TMEM
 // allocation + weight producer, warp 5 = MMA issuer.
 // Precision: bf16 operands, fp32 accumulation / residual stream / biases -> within rtol 2e-2 of the reference's fp32 module.
@@ -53,6 +57,8 @@ struct NpArgs {
     int nstage, nsteps;
     NpStep st[kNpMaxSteps];
     uint32_t off_ring;
+    uint32_t cluster;    // CTAs sharing every weight stage by multicast (1, 2 or 4)
+    int ntiles;          // real row tiles; CTAs past them (the grid is padded to whole clusters) only keep the lockstep
 };
 
 __device__ __forceinline__ int np_chunk_rows(int n, int kp) {
@@ -71,12 +77,16 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
     __shared__ uint32_t tmem_base_sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x / a.tiles_per_b;
-    const int row0 = (blockIdx.x % a.tiles_per_b) * kTcM;
+    const uint32_t C = a.cluster;
+    const uint32_t rank = C > 1 ? cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << C) - 1u);
+    const bool real_tile = (int)blockIdx.x < a.ntiles;
+    const int b = real_tile ? blockIdx.x / a.tiles_per_b : 0;
+    const int row0 = real_tile ? (blockIdx.x % a.tiles_per_b) * kTcM : a.N;   // a padding CTA owns no valid row
     if (tid == 0) {
         for (int s = 0; s < kNpStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], C);   // every CTA of the cluster commits to every CTA's empty barrier
         }
         mbar_init(&mma_bar, 1);
         mbar_init(&a_bar, kTcEpiThreads);
@@ -86,6 +96,7 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (C > 1) cluster_sync_all();  // every peer's barriers exist before anything is multicast to them
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp == 4) {
@@ -99,9 +110,15 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
                     if (it >= kNpStages) mbar_wait(&empty_bar[stage], ((it / kNpStages) - 1u) & 1u);
                     const int rowsk = min(ck, st.kp - k0);
                     const uint32_t bytes = (uint32_t)rowsk * st.n * 2u;
-                    mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                    tma_load_1d(smem + a.off_ring + stage * kNpStageBytes, a.blob + st.w_off + (size_t)k0 * st.n * 2u, bytes,
-                                &full_bar[stage]);
+                    mbar_arrive_expect_tx(&full_bar[stage], bytes);   // the whole stage: this CTA's slice + the peers'
+                    unsigned char* dst = smem + a.off_ring + stage * kNpStageBytes;
+                    const unsigned char* src = a.blob + st.w_off + (size_t)k0 * st.n * 2u;
+                    if (C > 1) {
+                        const uint32_t slice = bytes / C;   // bytes is a multiple of 512
+                        tma_load_1d_multicast(dst + rank * slice, src + rank * slice, slice, &full_bar[stage], cmask);
+                    } else {
+                        tma_load_1d(dst, src, bytes, &full_bar[stage]);
+                    }
                 }
             }
         }
@@ -133,7 +150,8 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
                         const uint64_t bd = umma_smem_desc(w_addr + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
                         umma_bf16(d_addr, ad, bd, idesc, st.acc || q > 0);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (C > 1) umma_commit_multicast(&empty_bar[stage], cmask);
+                    else umma_commit(&empty_bar[stage]);
                 }
                 if (st.epi) {
                     umma_commit(&mma_bar);
@@ -221,6 +239,7 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast or commit into it
     if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
@@ -456,7 +475,24 @@ extern "C" int pcst_noise_predictor_f32(const float* points, const int64_t* time
     a.off_ring = p.off_ring;
     PCST_CUDA(cudaFuncSetAttribute(noise_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     const long tiles = (long)B * a.tiles_per_b;
-    PCST_CHECK_ARG(tiles < (1L << 31), "too many rows");
-    noise_mlp_kernel<<<(unsigned)tiles, kTcThreads, p.smem_bytes, stream>>>(a);
-    return check_cuda(cudaGetLastError(), "noise_mlp_kernel");
+    PCST_CHECK_ARG(tiles < (1L << 30), "too many rows");
+    int C = tuning("noise.cluster", 0);
+    if (C != 2 && C != 4) C = 1;   // measured (profiles/r02/noise_cluster_ab.log): the serial MMA -> epilogue chain per tile, not
+                                   // the L2, bounds the kernel today, and the cluster's lockstep costs 18 %: opt-in
+    a.cluster = (uint32_t)C;
+    a.ntiles = (int)tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((tiles + C - 1) / C * C));
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PCST_CUDA(cudaLaunchKernelEx(&cfg, noise_mlp_kernel, a));
+    return PCST_OK;
 }

@@ -105,6 +105,17 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
 }
+// 1-D TMA bulk copy global -> the SAME shared-memory offset of every CTA in cta_mask (one L2 read serves the cluster);
+// completion is counted on the mbarrier at the same offset in each destination CTA.
+__device__ __forceinline__ void tma_load_1d_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                      uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+
 inline uint32_t tmem_cols_pow2(int cols) { return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512; }
 
 }  // namespace pcst
