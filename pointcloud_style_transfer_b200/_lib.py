@@ -86,6 +86,7 @@ SIGNATURES = {
                                          POINTER(Mlp3Train), c_int, c_void_p, c_size_t, c_void_p, POINTER(Mlp3Grads), c_void_p,
                                          c_void_p, c_size_t, c_void_p]),
     "pcst_noise_predictor_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcst_noise_predictor_pack_launches": (c_int, [c_int, c_int, c_int]),
     "pcst_noise_predictor_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_noise_predictor_pack_f32": (c_int, [POINTER(NoiseMlp), c_void_p, c_size_t, c_void_p]),
     "pcst_noise_predictor_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

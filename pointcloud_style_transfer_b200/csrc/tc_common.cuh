@@ -54,6 +54,12 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uin
                  "r"(src_cta_addr), "r"(bytes), "r"(bar_cluster_addr)
                  : "memory");
 }
+// One lane of a converged warp (the same one every time for a given warp): the issuer of single-thread instructions.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
@@ -113,6 +119,53 @@ __device__ __forceinline__ void tma_load_1d_multicast(void* smem_dst, const void
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
             smem_u32(smem_dst)),
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+
+// ---- the same primitives on precomputed shared-window addresses.  In a cluster launch a generic pointer to a __shared__
+// object is converted with S2UR SR_CgaCtaId at EVERY use; an address formed once and hidden from the optimiser is not.
+__device__ __forceinline__ uint32_t tc_opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast_addr(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_addr(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_multicast_addr(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar,
+                                                           uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_dst),
+        "l"(gmem_src), "r"(bytes), "r"(bar), "h"(cta_mask)
         : "memory");
 }
 

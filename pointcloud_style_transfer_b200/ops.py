@@ -706,7 +706,7 @@ def sa_mlp_train(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor]
 # ------------------------------------------------------------------------- NoisePredictor (fused per-point MLP chain)
 
 KERNELS_PER_CALL["pcst_noise_predictor_f32"] = 2          # conditioning prep + the fused chain
-KERNELS_PER_CALL["pcst_noise_predictor_pack_f32"] = 40
+KERNELS_PER_CALL["pcst_noise_predictor_pack_f32"] = 0      # size dependent: pcst_noise_predictor_pack_launches
 
 
 def noise_predictor_supported(feature_dim: int, time_dim: int, nblocks: int) -> bool:
@@ -741,7 +741,8 @@ def noise_predictor_pack(pe, time_proj, style_proj, blocks, out) -> Tensor:
         if nb == 0:
             raise ValueError("noise_predictor_pack: unsupported sizes (feature_dim a multiple of 16 in [16, 256], <= 8 blocks)")
         packed = torch.empty(nb, dtype=torch.uint8, device=dev)
-        _call("pcst_noise_predictor_pack_f32", ctypes.byref(m), _p(packed), nb, _stream())
+        _call("pcst_noise_predictor_pack_f32", ctypes.byref(m), _p(packed), nb, _stream(),
+              kernels=int(lib.pcst_noise_predictor_pack_launches(m.feature_dim, m.time_dim, m.nblocks)))
     return packed
 
 
