@@ -131,7 +131,10 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     __shared__ __align__(8) uint64_t x_bar[2]; // the peers' activation slices of an epilogue have landed (by event parity)
     __shared__ uint32_t tmem_base_sh;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp-uniform FOR THE COMPILER: the role branches below become uniform branches and the single-lane roles' loop
+    // counters, table reads and descriptors live in uniform registers (see the MMA issuer)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t C = a.cluster;
     const uint32_t rank = C > 1 ? cluster_ctarank() : 0;
     const int tile_first = (int)(blockIdx.x / C), tile_stride = (int)(gridDim.x / C);
@@ -146,7 +149,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&mma_bar, C);  // every CTA of the cluster commits to every CTA's barrier
-        mbar_init(&a_bar, kTcEpiThreads);
+        mbar_init(&a_bar, kTcEpiThreads / 32);  // one arrival per epilogue warp (after __syncwarp)
         mbar_init(&x_bar[0], 1);
         mbar_init(&x_bar[1], 1);
         fence_mbar_init();
@@ -163,77 +166,130 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     if (C > 1) cluster_sync_all();  // every peer's barriers exist before anything is sent to them
     const uint32_t tmem_base = tmem_base_sh;
 
+    // shared-window addresses formed once: a generic pointer to a __shared__ object is re-derived with S2UR SR_CgaCtaId at
+    // every use in a cluster launch
+    const uint32_t smem_base = tc_opaque_u32(smem_u32(smem));
+    const uint32_t full0 = tc_opaque_u32(smem_u32(&full_bar[0])), empty0 = tc_opaque_u32(smem_u32(&empty_bar[0]));
+    const uint32_t mma_bar_a = tc_opaque_u32(smem_u32(&mma_bar)), a_bar_a = tc_opaque_u32(smem_u32(&a_bar));
+    const uint32_t x_bar_a = tc_opaque_u32(smem_u32(&x_bar[0]));
+    const bool relaxed = kWalk && a.relaxed;
+    auto wait_relaxed = [&](uint32_t bar, uint32_t parity) {
+        if (relaxed) {
+            uint32_t ok;
+            for (;;) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(bar), "r"(parity)
+                    : "memory");
+                if (ok) break;
+                __nanosleep(64);
+            }
+        } else {
+            mbar_wait_addr(bar, parity);
+        }
+    };
+
     if (warp == 4) {
         // ================= weight producer =================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // the ring never drains between tiles: the next tile's first chunks load under this tile's epilogues
-            uint32_t it = 0;
+            const uint32_t nstages = (uint32_t)a.nstages;
+            uint32_t stage = 0, round = 0;   // ring position; how often the ring has wrapped
             for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles)
                 for (int s = 0; s < a.nsteps; ++s) {
                     const TcStep& st = a.st[s];
                     const unsigned char* src = a.blob + st.w_off + (size_t)rank * st.w_stride;
-                    for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
-                        const uint32_t stage = it % a.nstages;
-                        if (it >= a.nstages) mbar_wait_relaxed(&empty_bar[stage], ((it / a.nstages) - 1u) & 1u, kWalk && a.relaxed);
-                        const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
-                        const uint32_t bytes = (uint32_t)ck * st.n * 2u;
-                        mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                        tma_load_1d(smem + a.off_ring + stage * a.stage_bytes, src + (size_t)k0 * st.n * 2u, bytes,
-                                    &full_bar[stage]);
+                    const uint32_t kp = (uint32_t)st.kp, ckf = (uint32_t)st.ck, row_bytes = (uint32_t)st.n * 2u;
+                    for (uint32_t k0 = 0; k0 < kp; k0 += ckf) {
+                        if (round > 0) wait_relaxed(empty0 + stage * 8u, (round - 1u) & 1u);
+                        const uint32_t bytes = min(ckf, kp - k0) * row_bytes;
+                        mbar_expect_tx_addr(full0 + stage * 8u, bytes);
+                        tma_load_1d_addr(smem_base + a.off_ring + stage * a.stage_bytes, src, bytes, full0 + stage * 8u);
+                        src += bytes;
+                        if (++stage == nstages) { stage = 0; ++round; }
                     }
                 }
         }
     } else if (warp == 5) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // Events on a_bar, per tile: the gather, then one per epilogue EXCEPT the tile's last (pooled) one -- the
-            // next tile's gather event follows it in the same threads and stands for both (two arrivals nobody waits
-            // between would let the barrier run two phases ahead of this thread's parity wait).
-            uint32_t it = 0, seen = 0, need = 0;
-            uint32_t xseen = 0;                   // operand-writing epilogues whose REMOTE slices have been awaited
-            for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
-                ++need;                           // this tile's gather
-                int xstep = 0;                    // step scanned up to while counting those epilogues
-                for (int s = 0; s < a.nsteps; ++s) {
-                    const TcStep& st = a.st[s];
-                    while (seen < need) {
-                        mbar_wait_relaxed(&a_bar, seen & 1u, kWalk && a.relaxed);
-                        ++seen;
+        // The whole warp walks the loop converged and one elected lane issues.  Issued from a lone lane of a divergent
+        // branch, every tcgen05.mma operand is a per-thread value for the compiler: a register -> uniform-register move
+        // each and an ELECT / BRA.U.ANY waterfall loop around every UTCHMMA, ~200 cycles per MMA against a tensor-pipe
+        // floor of 32-128 (measured on the denoiser kernel, csrc/noise_mlp_tc.cu).  Converged, the loop runs on the uniform
+        // datapath and a stage's MMAs issue back to back.
+        //
+        // Events on a_bar, per tile: the gather, then one per epilogue EXCEPT the tile's last (pooled) one -- the
+        // next tile's gather event follows it in the same threads and stands for both (two arrivals nobody waits
+        // between would let the barrier run two phases ahead of this thread's parity wait).
+        const bool leader = elect_one_sync();
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);     // SBO = 128 B; descriptor version 1 (bit 46)
+        const uint32_t a_step = (2u * kTcM * 16u) >> 4;        // one K = 16 slice of A: two K groups of 128 rows
+        const uint32_t ring_lo = (smem_base + a.off_ring) >> 4, stage_lo = a.stage_bytes >> 4;
+        const uint32_t nstages = (uint32_t)a.nstages;
+        uint32_t stage = 0, round = 0, seen = 0, need = 0;
+        uint32_t xseen = 0;                   // operand-writing epilogues whose REMOTE slices have been awaited
+        for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
+            ++need;                           // this tile's gather
+            int xstep = 0;                    // step scanned up to while counting those epilogues
+            for (int s = 0; s < a.nsteps; ++s) {
+                const TcStep& st = a.st[s];
+                while (seen < need) {
+                    wait_relaxed(a_bar_a, seen & 1u);
+                    ++seen;
+                }
+                if (C > 1) {
+                    // every operand-writing epilogue before this step: (C - 1) peers each push 128 x n x 2 bytes
+                    for (; xstep < s; ++xstep) {
+                        if (a.st[xstep].epi != 1) continue;
+                        const uint32_t xb = x_bar_a + (xseen & 1u) * 8u;
+                        if (leader) mbar_expect_tx_addr(xb, (C - 1u) * (uint32_t)a.st[xstep].n * (kTcM * 2u));
+                        __syncwarp();
+                        mbar_wait_addr(xb, (xseen >> 1) & 1u);
+                        ++xseen;
                     }
-                    if (C > 1) {
-                        // every operand-writing epilogue before this step: (C - 1) peers each push 128 x n x 2 bytes
-                        for (; xstep < s; ++xstep) {
-                            if (a.st[xstep].epi != 1) continue;
-                            uint64_t* xb = &x_bar[xseen & 1u];
-                            mbar_arrive_expect_tx(xb, (C - 1u) * (uint32_t)a.st[xstep].n * (kTcM * 2u));
-                            mbar_wait(xb, (xseen >> 1) & 1u);
-                            ++xseen;
-                        }
-                    }
+                }
+                tc_fence_after();
+                const uint32_t n = (uint32_t)st.n, kp = (uint32_t)st.kp, ckf = (uint32_t)st.ck;
+                const uint32_t idesc = umma_idesc_bf16(kTcM, (int)n);
+                const uint32_t d_addr = tmem_base + st.tmem_col;
+                const uint32_t w_step = n * 2u;                // one K = 16 slice of the weights, 16-byte units
+                const uint32_t w_lbo = n << 16;                // LBO = n * 16 bytes
+                uint32_t a_lo = (((smem_base + st.a_off) >> 4) & 0x3FFFu) | (((kTcM * 16u) >> 4) << 16);
+                uint32_t accum = st.acc;
+                for (uint32_t k0 = 0; k0 < kp; k0 += ckf) {
+                    mbar_wait_addr(full0 + stage * 8u, round & 1u);
                     tc_fence_after();
-                    const uint32_t idesc = umma_idesc_bf16(kTcM, st.n);
-                    const uint32_t a_addr = smem_u32(smem + st.a_off);
-                    const uint32_t lbo_a = kTcM * 16, lbo_w = (uint32_t)st.n * 16;
-                    const uint32_t d_addr = tmem_base + st.tmem_col;
-                    for (int k0 = 0; k0 < st.kp; k0 += st.ck, ++it) {
-                        const uint32_t stage = it % a.nstages;
-                        mbar_wait(&full_bar[stage], (it / a.nstages) & 1u);
-                        tc_fence_after();
-                        const uint32_t w_addr = smem_u32(smem + a.off_ring + stage * a.stage_bytes);
-                        const int ck = st.kp - k0 < st.ck ? st.kp - k0 : st.ck;
-                        for (int kk = 0; kk < ck / 16; ++kk) {
-                            const int q = k0 / 16 + kk;  // K16 step inside the A operand
-                            const uint64_t ad = umma_smem_desc(a_addr + (uint32_t)q * 2u * lbo_a, lbo_a, 128);
-                            const uint64_t bd = umma_smem_desc(w_addr + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
-                            umma_bf16(d_addr, ad, bd, idesc, st.acc || q > 0);
+                    const uint32_t nk = min(ckf, kp - k0) >> 4;
+                    if (leader) {
+                        const uint32_t w_lo = ((ring_lo + stage * stage_lo) & 0x3FFFu) | w_lbo;
+                        auto mma = [&](uint32_t kk, bool acc) {
+                            umma_bf16(d_addr, ((uint64_t)desc_hi << 32) | (a_lo + kk * a_step),
+                                      ((uint64_t)desc_hi << 32) | (w_lo + kk * w_step), idesc, acc);
+                        };
+                        if (nk == 4) {
+                            mma(0, accum != 0); mma(1, true); mma(2, true); mma(3, true);
+                        } else if (nk == 2) {
+                            mma(0, accum != 0); mma(1, true);
+                        } else {
+                            for (uint32_t kk = 0; kk < nk; ++kk) mma(kk, (accum | kk) != 0);
                         }
-                        umma_commit(&empty_bar[stage]);  // the stage is free once these MMAs have read it
+                        umma_commit_addr(empty0 + stage * 8u);  // the stage is free once these MMAs have read it
                     }
-                    if (st.epi) {
-                        if (C > 1) umma_commit_multicast(&mma_bar, (uint16_t)((1u << C) - 1u));
-                        else umma_commit(&mma_bar);
-                        if (s != a.nsteps - 1) ++need;
+                    __syncwarp();
+                    a_lo += nk * a_step;
+                    accum = 1;
+                    if (++stage == nstages) { stage = 0; ++round; }
+                }
+                if (st.epi) {
+                    if (leader) {
+                        if (C > 1) umma_commit_multicast_addr(mma_bar_a, (uint16_t)((1u << C) - 1u));
+                        else umma_commit_addr(mma_bar_a);
                     }
+                    __syncwarp();
+                    if (s != a.nsteps - 1) ++need;
                 }
             }
         }
@@ -329,12 +385,13 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             if (tile == tile_first) epi_bar_sync();  // the scale/shift tables are complete for every epilogue thread
             tc_fence_before();    // (later tiles) the previous tile's accumulator reads precede the MMAs this releases
-            mbar_arrive(&a_bar);  // the layer-0 operand is in place
+            __syncwarp();
+            if (lane == 0) mbar_arrive_addr(a_bar_a);  // the layer-0 operand is in place
 
             for (int s = 0; s < a.nsteps; ++s) {
                 const TcStep& st = a.st[s];
                 if (!st.epi) continue;
-                mbar_wait(&mma_bar, mma_phase & 1u);  // all C CTAs have finished the MMAs up to this step
+                mbar_wait_addr(mma_bar_a, mma_phase & 1u);  // all C CTAs have finished the MMAs up to this step
                 ++mma_phase;
                 tc_fence_after();
                 if (stamp && nstamp < 14) stamp[nstamp++] = clock64();
@@ -379,7 +436,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                         epi_bar_sync();
                         if (tid == 0) {
                             const uint32_t src = smem_u32(outp), bytes = (uint32_t)st.n * (kTcM * 2u);
-                            const uint32_t bar = smem_u32(&x_bar[xev & 1u]);
+                            const uint32_t bar = x_bar_a + (xev & 1u) * 8u;
                             for (uint32_t q = 0; q < C; ++q)
                                 if (q != rank) bulk_copy_to_peer(mapa_shared(src, q), src, bytes, mapa_shared(bar, q));
                         }
@@ -492,7 +549,8 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                 if (stamp && nstamp < 14) stamp[nstamp++] = clock64();
                 if (s != a.nsteps - 1) {  // the last (pooled) step: the next tile's gather event stands for it
                     tc_fence_before();
-                    mbar_arrive(&a_bar);  // operand written / accumulator drained: later steps may proceed
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_addr(a_bar_a);  // operand written / accumulator drained: later steps may proceed
                 }
             }
         }
