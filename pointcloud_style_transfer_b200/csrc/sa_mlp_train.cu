@@ -249,7 +249,8 @@ train_gemm_kernel(const __grid_constant__ TgArgs a) {
     __shared__ __align__(8) uint64_t mma_bar;  // the MMAs of a K panel have completed
     __shared__ uint32_t tmem_base_sh;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform role branches)
     const int row0 = blockIdx.x * kTcM;
     if (tid == 0) {
         for (int s = 0; s < kTrStages; ++s) {
@@ -296,45 +297,55 @@ train_gemm_kernel(const __grid_constant__ TgArgs a) {
             }
         }
     } else if (warp == 5) {
-        // ---- MMA issuer ----
-        if (lane == 0) {
-            uint32_t it = 0;
-            const uint32_t a_addr = smem_u32(smem + a.off_a);
-            const uint32_t lbo_a = kTcM * 16;
-            for (int pan = 0; pan < npan; ++pan) {
-                const int klen = min(kpan, a.kp - pan * kpan);
-                mbar_wait(&a_bar, pan & 1);
-                tc_fence_after();
-                for (int ch = 0; ch < nchunks; ++ch) {
-                    const int nc = min(256, a.n - ch * 256);
-                    const int ck = tg_chunk_rows(nc, klen, a.split);
-                    const uint32_t idesc = umma_idesc_bf16(kTcM, nc);
-                    const uint32_t lbo_w = (uint32_t)nc * 16;
-                    const uint32_t d_addr = tmem_base + (uint32_t)ch * 256u;
-                    for (int k0 = 0; k0 < klen; k0 += ck, ++it) {
-                        const uint32_t stage = it % kTrStages;
-                        mbar_wait(&full_bar[stage], (it / kTrStages) & 1u);
-                        tc_fence_after();
-                        const uint32_t w_addr = smem_u32(smem + a.off_ring + stage * kTrStageBytes);
-                        const int rowsk = min(ck, klen - k0);
-                        const uint32_t w_lo = (uint32_t)rowsk * nc * 2u;  // the lo copy follows the hi copy inside the stage
-                        for (int kk = 0; kk < rowsk / 16; ++kk) {
-                            const int q = k0 / 16 + kk;  // K16 step inside the panel
-                            const uint64_t ad = umma_smem_desc(a_addr + (uint32_t)q * 2u * lbo_a, lbo_a, 128);
-                            const uint64_t bd = umma_smem_desc(w_addr + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
-                            umma_bf16(d_addr, ad, bd, idesc, pan > 0 || q > 0);
-                            if (a.split) {
-                                const uint64_t adl = umma_smem_desc(a_addr + a.a_bytes + (uint32_t)q * 2u * lbo_a, lbo_a, 128);
-                                const uint64_t bdl = umma_smem_desc(w_addr + w_lo + (uint32_t)kk * 2u * lbo_w, lbo_w, 128);
-                                umma_bf16(d_addr, adl, bd, idesc, true);
-                                umma_bf16(d_addr, ad, bdl, idesc, true);
+        // ---- MMA issuer: the whole warp converged, one elected lane issues (uniform datapath; see sa_mlp_tc.cu) ----
+        const bool leader = elect_one_sync();
+        const uint32_t smem_base = tc_opaque_u32(smem_u32(smem));
+        const uint32_t full0 = tc_opaque_u32(smem_u32(&full_bar[0])), empty0 = tc_opaque_u32(smem_u32(&empty_bar[0]));
+        const uint32_t a_bar_a = tc_opaque_u32(smem_u32(&a_bar)), mma_bar_a = tc_opaque_u32(smem_u32(&mma_bar));
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);     // SBO = 128 B; descriptor version 1 (bit 46)
+        const uint32_t a_step = (2u * kTcM * 16u) >> 4;        // one K = 16 slice of A
+        const uint32_t a_base = (((smem_base + a.off_a) >> 4) & 0x3FFFu) | (((kTcM * 16u) >> 4) << 16);
+        const uint32_t a_lo_copy = a.a_bytes >> 4;             // the lo copy of the operand (split mode)
+        const uint32_t ring_lo = (smem_base + a.off_ring) >> 4;
+        const bool split = a.split != 0;
+        uint32_t stage = 0, round = 0;
+        for (int pan = 0; pan < npan; ++pan) {
+            const int klen = min(kpan, a.kp - pan * kpan);
+            mbar_wait_addr(a_bar_a, pan & 1);
+            tc_fence_after();
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const uint32_t nc = (uint32_t)min(256, a.n - ch * 256);
+                const uint32_t ck = (uint32_t)tg_chunk_rows((int)nc, klen, a.split);
+                const uint32_t idesc = umma_idesc_bf16(kTcM, (int)nc);
+                const uint32_t w_lbo = nc << 16, w_step = nc * 2u;
+                const uint32_t d_addr = tmem_base + (uint32_t)ch * 256u;
+                uint32_t a_lo = a_base;
+                for (uint32_t k0 = 0; k0 < (uint32_t)klen; k0 += ck) {
+                    mbar_wait_addr(full0 + stage * 8u, round & 1u);
+                    tc_fence_after();
+                    const uint32_t rowsk = min(ck, (uint32_t)klen - k0), nk = rowsk >> 4;
+                    if (leader) {
+                        const uint32_t w_lo = ((ring_lo + stage * (kTrStageBytes >> 4)) & 0x3FFFu) | w_lbo;
+                        const uint32_t w_lo_copy = (rowsk * nc * 2u) >> 4;  // the lo copy follows the hi copy inside the stage
+                        const bool first = pan == 0 && k0 == 0;
+                        for (uint32_t kk = 0; kk < nk; ++kk) {
+                            const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + kk * a_step);
+                            const uint64_t bd = ((uint64_t)desc_hi << 32) | (w_lo + kk * w_step);
+                            umma_bf16(d_addr, ad, bd, idesc, !(first && kk == 0));
+                            if (split) {
+                                umma_bf16(d_addr, ad + a_lo_copy, bd, idesc, true);
+                                umma_bf16(d_addr, ad, bd + w_lo_copy, idesc, true);
                             }
                         }
-                        umma_commit(&empty_bar[stage]);
+                        umma_commit_addr(empty0 + stage * 8u);
                     }
+                    __syncwarp();
+                    a_lo += nk * a_step;
+                    if (++stage == kTrStages) { stage = 0; ++round; }
                 }
-                umma_commit(&mma_bar);
             }
+            if (leader) umma_commit_addr(mma_bar_a);
+            __syncwarp();
         }
     } else {
         // ---- operand build + epilogue: thread = row = TMEM lane ----
@@ -435,7 +446,8 @@ train_wgrad_kernel(const __grid_constant__ WgArgs a) {
     __shared__ __align__(8) uint64_t mma_bar;    // the tile's MMAs have read them
     __shared__ uint32_t tmem_base_sh;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform role branches)
     const int mb = blockIdx.y;
     const int tiles = (a.rows + a.tr - 1) / a.tr;
     const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -454,29 +466,39 @@ train_wgrad_kernel(const __grid_constant__ WgArgs a) {
     const uint32_t lbo_a = (kTcM + 1) * 16, lbo_b = (uint32_t)(a.kp + 1) * 16;
 
     if (warp == 5) {
-        if (lane == 0) {
-            const uint32_t a_addr = smem_u32(smem + a.off_a), b_addr = smem_u32(smem + a.off_b);
-            for (int t = 0; t < my_tiles; ++t) {
-                mbar_wait(&built_bar, t & 1);
-                tc_fence_after();
+        // whole warp converged, one elected lane issues (uniform datapath; see sa_mlp_tc.cu)
+        const bool leader = elect_one_sync();
+        const uint32_t smem_base = tc_opaque_u32(smem_u32(smem));
+        const uint32_t built_a = tc_opaque_u32(smem_u32(&built_bar)), mma_bar_a = tc_opaque_u32(smem_u32(&mma_bar));
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);     // SBO = 128 B; descriptor version 1 (bit 46)
+        const uint32_t a_base = (((smem_base + a.off_a) >> 4) & 0x3FFFu) | ((lbo_a >> 4) << 16);
+        const uint32_t b_base = (((smem_base + a.off_b) >> 4) & 0x3FFFu) | ((lbo_b >> 4) << 16);
+        const uint32_t a_step = (2u * lbo_a) >> 4, b_step = (2u * lbo_b) >> 4;
+        const uint32_t a_copy = a.a_bytes >> 4, b_copy = a.b_bytes >> 4;
+        const bool split = a.split != 0;
+        const uint32_t nq = (uint32_t)a.tr / 16u;
+        for (int t = 0; t < my_tiles; ++t) {
+            mbar_wait_addr(built_a, t & 1);
+            tc_fence_after();
+            if (leader) {
                 for (int n0 = 0; n0 < a.kp; n0 += 256) {
                     const int nc = min(256, a.kp - n0);
                     const uint32_t idesc = umma_idesc_bf16(kTcM, nc);
-                    for (int q = 0; q < a.tr / 16; ++q) {
-                        const uint32_t ao = (uint32_t)q * 2u * lbo_a, bo = (uint32_t)n0 * 16u + (uint32_t)q * 2u * lbo_b;
-                        const uint64_t ad = umma_smem_desc(a_addr + ao, lbo_a, 128);
-                        const uint64_t bd = umma_smem_desc(b_addr + bo, lbo_b, 128);
-                        umma_bf16(tmem_base + (uint32_t)n0, ad, bd, idesc, t > 0 || q > 0);
-                        if (a.split) {
-                            const uint64_t adl = umma_smem_desc(a_addr + a.a_bytes + ao, lbo_a, 128);
-                            const uint64_t bdl = umma_smem_desc(b_addr + a.b_bytes + bo, lbo_b, 128);
-                            umma_bf16(tmem_base + (uint32_t)n0, adl, bd, idesc, true);
-                            umma_bf16(tmem_base + (uint32_t)n0, ad, bdl, idesc, true);
+                    const uint32_t d_addr = tmem_base + (uint32_t)n0;
+                    const uint32_t b_lo = b_base + (uint32_t)n0;   // n0 rows of 16 bytes
+                    for (uint32_t q = 0; q < nq; ++q) {
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_base + q * a_step);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + q * b_step);
+                        umma_bf16(d_addr, ad, bd, idesc, t > 0 || q > 0);
+                        if (split) {
+                            umma_bf16(d_addr, ad + a_copy, bd, idesc, true);
+                            umma_bf16(d_addr, ad, bd + b_copy, idesc, true);
                         }
                     }
                 }
-                umma_commit(&mma_bar);
+                umma_commit_addr(mma_bar_a);
             }
+            __syncwarp();
         }
     } else if (warp < 4) {
         const int m = tid;
