@@ -203,13 +203,18 @@ vox_scatter_kernel(const unsigned int* __restrict__ kin, const unsigned int* __r
 
 // ---- runs of equal keys -> one truncated float32 mean of the member indices per run ---------------------------
 __global__ void __launch_bounds__(kSortThreads)
-vox_heads_kernel(const unsigned int* __restrict__ keys, int N, unsigned int* __restrict__ gcount, int ntiles) {
+vox_heads_kernel(const unsigned int* __restrict__ keys, int N, unsigned int* __restrict__ gcount, int ntiles,
+                 unsigned long long* __restrict__ sum, unsigned int* __restrict__ cnt) {
     __shared__ unsigned int wsum[kSortWarps];
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int* k = keys + (size_t)b * N;
     const int lo = tile * kSortTile, hi = min(lo + kSortTile, N);
     unsigned int heads = 0;
-    for (int i = lo + tid; i < hi; i += kSortThreads) heads += (i == 0 || k[i] != k[i - 1]) ? 1u : 0u;
+    for (int i = lo + tid; i < hi; i += kSortThreads) {
+        heads += (i == 0 || k[i] != k[i - 1]) ? 1u : 0u;
+        sum[(size_t)b * N + i] = 0ull;   // the per-run accumulators of vox_runs_kernel (run ranks are < N)
+        cnt[(size_t)b * N + i] = 0u;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) heads += __shfl_xor_sync(0xffffffffu, heads, o);
     if (lane == 0) wsum[warp] = heads;
@@ -221,12 +226,18 @@ vox_heads_kernel(const unsigned int* __restrict__ keys, int N, unsigned int* __r
     }
 }
 
+// Every element adds its index to the accumulator of its run (rank = number of run heads up to and including it, minus
+// one): a warp first reduces each stretch of 32 consecutive elements that share a run (prefix sum over the lanes, one
+// difference per segment) and the segment's last lane issues ONE atomic for it.  A run of any length therefore costs
+// length / 32 atomics spread over its warps -- the first version let the head's thread walk its run alone, and a LiDAR
+// scan's near-range voxels hold thousands of points: 307 us of a 120k-point call were that tail.
 __global__ void __launch_bounds__(kSortThreads)
 vox_runs_kernel(const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals, int N,
-                const unsigned int* __restrict__ gcount, int ntiles, int64_t* __restrict__ rep, int* __restrict__ count) {
+                const unsigned int* __restrict__ gcount, int ntiles, unsigned long long* __restrict__ sum,
+                unsigned int* __restrict__ cnt, int* __restrict__ count) {
     __shared__ unsigned int wsum[kSortWarps];
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned int lt_mask = (1u << lane) - 1u;
+    const unsigned int le_mask = lane == 31 ? 0xffffffffu : (2u << lane) - 1u;
     const unsigned int* k = keys + (size_t)b * N;
     const unsigned int* v = vals + (size_t)b * N;
     unsigned int before = 0, total = 0;
@@ -250,22 +261,40 @@ vox_runs_kernel(const unsigned int* __restrict__ keys, const unsigned int* __res
     __syncthreads();
     unsigned int run = before;
     for (int w = 0; w < warp; ++w) run += wsum[w];
-    int64_t* out = rep + (size_t)b * N;
+    unsigned long long* osum = sum + (size_t)b * N;
+    unsigned int* ocnt = cnt + (size_t)b * N;
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
         const int i = wlo + r * 32 + lane;
-        if ((hb[r] >> lane) & 1u) {
-            long long s = 0, c = 0;
-            const unsigned int key = k[i];
-            for (int j = i; j < N && k[j] == key; ++j) {  // runs are short (a few points per voxel); may cross tiles
-                s += v[j];
-                ++c;
-            }
-            // (sum / bincount).long() with int64 operands: torch true-divides in float32 (:93)
-            out[run + __popc(hb[r] & lt_mask)] = (int64_t)__fdiv_rn((float)s, (float)c);
+        const bool in = i < N;
+        unsigned int pre = in ? v[i] : 0u;   // inclusive prefix sum over the lanes (32 indices < 2^27: no overflow)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+        }
+        const unsigned int mine_heads = hb[r] & le_mask;
+        const int seg = mine_heads ? 31 - __clz(mine_heads) : 0;       // first lane of this lane's segment
+        const unsigned int below = __shfl_sync(0xffffffffu, pre, seg > 0 ? seg - 1 : 0);
+        const bool last = in && (lane == 31 || ((hb[r] >> (lane + 1)) & 1u) || i + 1 >= N);
+        if (last) {
+            // lanes before the round's first head continue the previous run: rank run - 1 (element 0 is a head, so run >= 1)
+            const unsigned int rank = run + __popc(mine_heads) - 1u;
+            atomicAdd(osum + rank, (unsigned long long)(pre - (seg > 0 ? below : 0u)));
+            atomicAdd(ocnt + rank, (unsigned int)(lane - seg + 1));
         }
         run += __popc(hb[r]);
     }
+}
+
+// (sum / bincount).long() with int64 operands: torch true-divides in float32 (:93)
+__global__ void vox_finish_kernel(const unsigned long long* __restrict__ sum, const unsigned int* __restrict__ cnt, int N,
+                                  const int* __restrict__ count, int64_t* __restrict__ rep) {
+    const int b = blockIdx.y;
+    const int total = count[b];
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total; r += gridDim.x * blockDim.x)
+        rep[(size_t)b * N + r] =
+            (int64_t)__fdiv_rn((float)(long long)sum[(size_t)b * N + r], (float)(long long)cnt[(size_t)b * N + r]);
 }
 
 }  // namespace pcst
@@ -282,7 +311,7 @@ extern "C" int pcst_minmax_f32(const float* xyz, int B, int N, float* out, pcst_
 extern "C" size_t pcst_voxel_representatives_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
     const size_t ntiles = ((size_t)N + kSortTile - 1) / kSortTile;
-    return 4 * align_up((size_t)B * N * sizeof(unsigned int), 256) + align_up((size_t)B * 256 * ntiles * 4, 256) +
+    return 5 * align_up((size_t)B * N * sizeof(unsigned int), 256) + align_up((size_t)B * 256 * ntiles * 4, 256) +
            align_up((size_t)B * ntiles * 4, 256);
 }
 
@@ -303,7 +332,8 @@ extern "C" int pcst_voxel_representatives_f32(const float* xyz, int B, int N, co
     unsigned int* v0 = (unsigned int*)((char*)ws + stride);
     unsigned int* k1 = (unsigned int*)((char*)ws + 2 * stride);
     unsigned int* v1 = (unsigned int*)((char*)ws + 3 * stride);
-    unsigned int* ghist = (unsigned int*)((char*)ws + 4 * stride);
+    unsigned int* cnt = (unsigned int*)((char*)ws + 4 * stride);          // per-run member counts
+    unsigned int* ghist = (unsigned int*)((char*)ws + 5 * stride);
     unsigned int* gcount = (unsigned int*)((char*)ghist + align_up((size_t)B * 256 * ntiles * 4, 256));
     vox_hash_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(xyz, N, xyz_min, voxel_size, k0, v0);
     PCST_CUDA(cudaGetLastError());
@@ -316,8 +346,13 @@ extern "C" int pcst_voxel_representatives_f32(const float* xyz, int B, int N, co
         unsigned int* t = k0; k0 = k1; k1 = t;
         t = v0; v0 = v1; v1 = t;
     }
-    vox_heads_kernel<<<grid, kSortThreads, 0, stream>>>(k0, N, gcount, ntiles);
+    // the sorted pairs are back in the first two buffers (even number of passes): the other two, contiguous, hold the
+    // per-run 64-bit index sums
+    unsigned long long* sum = (unsigned long long*)k1;
+    vox_heads_kernel<<<grid, kSortThreads, 0, stream>>>(k0, N, gcount, ntiles, sum, cnt);
     PCST_CUDA(cudaGetLastError());
-    vox_runs_kernel<<<grid, kSortThreads, 0, stream>>>(k0, v0, N, gcount, ntiles, rep, count);
-    return check_cuda(cudaGetLastError(), "vox_runs_kernel");
+    vox_runs_kernel<<<grid, kSortThreads, 0, stream>>>(k0, v0, N, gcount, ntiles, sum, cnt, count);
+    PCST_CUDA(cudaGetLastError());
+    vox_finish_kernel<<<dim3((N + 1023) / 1024, B), 256, 0, stream>>>(sum, cnt, N, count, rep);
+    return check_cuda(cudaGetLastError(), "vox_finish_kernel");
 }

@@ -53,7 +53,7 @@ def _workspace(nbytes: int, device) -> Tensor:
 KERNELS_PER_CALL = {"pcst_l2_prefetch": 1, "pcst_fps_f32": 1, "pcst_ball_query_f32": 2, "pcst_square_distance_f32": 1,
                     "pcst_index_points_f32": 1, "pcst_index_points_bwd_f32": 1, "pcst_group_f32": 1,
                     "pcst_sa_mlp_max_f32": 3, "pcst_sa_mlp_pack_f32": 8, "pcst_nn_min_f32": 4, "pcst_nn_min_pair_f32": 4, "pcst_nn_min_pair_arg_f32": 6, "pcst_chamfer_bwd_f32": 1, "pcst_knn_f32": 1,
-                    "pcst_knn_interpolate_f32": 1, "pcst_minmax_f32": 1, "pcst_voxel_representatives_f32": 2}
+                    "pcst_knn_interpolate_f32": 1, "pcst_minmax_f32": 1, "pcst_voxel_representatives_f32": 12}  # hash, 4 x (count, scatter), heads, runs, finish
 launch_count = 0
 _event_log = None  # None = off; else list of (name, start_event, end_event)
 
