@@ -35,6 +35,8 @@ for rep in range(2):
         torch.manual_seed(1)
         enc_eval(x16)                                   # batched eval-mode MLP (8 x 16384)
         net(xc, tt, st)                                 # fused denoiser
+        lo_hi = ops.minmax(x)                           # voxel-grid representatives (radix sort + per-run means)
+        ops.voxel_representatives(x, lo_hi[:, :3].contiguous(), torch.full((1,), 0.01, device=dev))
         ops.knn(x, x, 9)                                # grid search (self query)
         rowmin, colmin = ops.nn_min_pair(x[:, :15000].contiguous(), y, 0)
         ops.chamfer_shard_finish(torch.stack([ops.chamfer_shard_pack(rowmin, colmin)] * 8), 120000, 0)
