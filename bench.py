@@ -444,11 +444,17 @@ def main():
             trainer.step(sim, real)
         l0 = ops.launch_count
         ms_tr = timed(lambda: trainer.step(sim, real), args.train_steps)
-        train_c4 = (statistics.mean(ms_tr), (ops.launch_count - l0) / (args.train_steps + 1), BL)
+        train_launches = (ops.launch_count - l0) / (args.train_steps + 1)
+        # the same step as ONE CUDA-graph replay (forward, backward, all-reduce, clip, AdamW, EMA)
+        for _ in range(2):
+            trainer.step_graphed(sim, real)
+        ms_tr_graph = timed(lambda: trainer.step_graphed(sim, real), args.train_steps)
+        train_c4 = (statistics.mean(ms_tr_graph), train_launches, BL, statistics.mean(ms_tr))
         # where the step's time goes (eager CUDA events around the C-ABI calls of one more step)
         ops.start_event_log()
         trainer.step(sim, real)
         tr_ops = {k: sum(v) for k, v in ops.stop_event_log().items()}
+        trainer.release()   # the captured graph holds NCCL kernels: drop it before the process group goes away
         del trainer
 
     # ---- denoiser (NoisePredictor) on the coarse clouds of one CFG step: 2 x 30 000 points ----
@@ -525,6 +531,7 @@ def main():
     t_sh_r1 = allmax(ch_sharded[2]) if ch_sharded is not None else None
     t_knn = allmax(knn_sharded) if knn_sharded is not None else None
     t_train = allmax(train_c4[0]) if train_c4 is not None else None
+    t_train_host = allmax(train_c4[3]) if train_c4 is not None else None
 
     if rank == 0:
         value = world * N_POINTS / (t_dev * 1e-3)
@@ -619,11 +626,16 @@ def main():
                           "(%d x 16384 on %d GPU%s)" % (BLc, BLc * world, world, "" if world == 1 else "s"),
                 "value": world * BLc * 16384 / (t_train * 1e-3), "unit": "points/s", "ms_per_step": t_train, "scaling": "weak",
                 "global_batch": BLc * world, "points_per_scan": 16384, "global_points": 4096,
+                "launch": "DiffusionTrainStep.step_graphed: one CUDA-graph replay per step (forward, backward, all-reduce, clip, "
+                          "AdamW, EMA); FPS start draws on the CPU generator before the replay",
+                "host_loop_ms_per_step": t_train_host,
+                "host_loop_note": "DiffusionTrainStep.step: the reference's host behaviour (kernels launched one by one, the loss "
+                                  "dict's three .item() syncs per step)",
                 "kernel_launches_per_step": train_c4[1], "op_ms_eager": tr_ops,
                 "what": "q_sample -> voxel downsample (device) -> style encoder fwd (native train-mode tcgen05 kernels, batch-stat "
                         "BatchNorm) -> denoiser (torch autocast bf16) -> L1 + 0.1 * Chamfer (native) -> backward (native dgrad / "
                         "wgrad / BatchNorm / Chamfer backward) -> one NCCL all-reduce of the flat gradient (10.2 MB) -> clip -> "
-                        "fused AdamW -> EMA; the loss dict's .item() calls of the reference are inside the step",
+                        "fused AdamW -> EMA",
                 "dtype": "bf16 GEMM operands (encoder: tcgen05 train kernels; denoiser: autocast), fp32 distances / statistics"}
         if denoiser is not None:
             rows_d = 2 * 30000

@@ -22,6 +22,10 @@ def chamfer_distance_chunked_optimized(pred: torch.Tensor, target: torch.Tensor,
 class DiffusionLoss(nn.Module):
     """models/losses.py:66-104: noise_weight * L1(noise) + chamfer_weight * mean_B(chamfer)."""
 
+    #: True = the reference's behaviour: ``loss_dict`` holds Python floats, i.e. three ``.item()`` host syncs per forward
+    #: (:93-102).  False = detached 0-dim device tensors, no sync (CUDA-graph capture of a training step needs this).
+    sync_items: bool = True
+
     def __init__(self, noise_weight: float = 1.0, chamfer_weight: float = 0.1):
         super().__init__()
         self.noise_weight = noise_weight
@@ -36,10 +40,10 @@ class DiffusionLoss(nn.Module):
         loss_dict = {}
         noise_loss = F.l1_loss(predicted_noise, actual_noise)
         total_loss = self.noise_weight * noise_loss
-        loss_dict['noise_loss'] = noise_loss.item()
+        loss_dict['noise_loss'] = noise_loss.item() if self.sync_items else noise_loss.detach()
         if self.chamfer_weight > 0 and predicted_points_coarse is not None and target_points_coarse is not None:
             chamfer_loss = torch.mean(chamfer_distance_chunked_optimized(predicted_points_coarse, target_points_coarse))
             total_loss += self.chamfer_weight * chamfer_loss
-            loss_dict['chamfer_loss'] = chamfer_loss.item()
-        loss_dict['total_loss'] = total_loss.item()
+            loss_dict['chamfer_loss'] = chamfer_loss.item() if self.sync_items else chamfer_loss.detach()
+        loss_dict['total_loss'] = total_loss.item() if self.sync_items else total_loss.detach()
         return total_loss, loss_dict

@@ -288,11 +288,17 @@ class PointNet2Encoder(nn.Module):
             sa.mlp_precision = int(precision)
         return self
 
+    #: FPS start indices (sa1, sa2) as static device buffers, read when ``forward`` gets no ``starts``: a captured CUDA
+    #: graph cannot contain the reference's CPU-generator draw (:36), so its owner refills these before every replay
+    static_starts: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+
     def forward(self, xyz: torch.Tensor, starts: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
         """``starts`` (optional) = the FPS start indices of sa1 / sa2 as device tensors; used by
         ``runtime.GraphedEncoder`` to keep the CPU RNG draws outside a captured CUDA graph."""
         B, N, C = xyz.shape
         points = None
+        if starts is None:
+            starts = self.static_starts   # set by a CUDA-graph runner that owns the encoder (train_step.DiffusionTrainStep)
         s1, s2 = starts if starts is not None else (None, None)
         if xyz.is_cuda and all(sa._fused_ok(xyz) for sa in (self.sa1, self.sa2, self.sa3)):
             return self._forward_overlapped(xyz, s1, s2)

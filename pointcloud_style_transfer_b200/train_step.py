@@ -13,6 +13,13 @@ What runs where:
   * gradient averaging across ranks: ONE NCCL all-reduce of a flat fp32 gradient buffer (2 549 827 parameters, 10.2 MB),
     the parameters' ``.grad`` tensors being views into it; then clip-by-norm 1.0, fused AdamW(0.9, 0.95) and the EMA update
     (:119-125).
+
+``step`` keeps the reference's host behaviour (the loss dictionary is read back with ``.item()`` three times per step,
+FPS start indices drawn on the CPU generator inside the forward).  ``step_graphed`` is the same arithmetic as ONE CUDA
+graph replay per step: a step is ~600 kernel launches of a few microseconds each and is bound by the host's launch rate
+otherwise.  The graph holds forward, backward, the NCCL all-reduce, clip, AdamW and EMA; the timestep / noise / dropout
+draws use the device generator as in the reference (:75-77, captured as graph-safe Philox offsets); the two FPS start
+draws stay on the CPU generator (reference :36) and are copied into static buffers before each replay.
 """
 from typing import Dict, Optional, Tuple
 
@@ -63,10 +70,11 @@ class DiffusionTrainStep:
         self.flat_grad = attach_flat_grad(params)   # every .grad is a view: the cross-rank average is one collective
         self.params = params
         self.optimizer = torch.optim.AdamW(params, lr=config.learning_rate, weight_decay=config.weight_decay, betas=(0.9, 0.95),
-                                           fused=True)
+                                           fused=True, capturable=True)   # capturable: the step counter lives on the device
         self.ema = [p.detach().clone() for p in params]
         self.ema_decay = getattr(config, "ema_decay", 0.999)
         self.clip = 1.0                                                                      # trainer.py:61
+        self._graph = None
 
     def loss(self, sim_points: torch.Tensor, real_points: torch.Tensor, t: Optional[torch.Tensor] = None,
              noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Dict[str, float]]:
@@ -105,3 +113,80 @@ class DiffusionTrainStep:
         self.optimizer.zero_grad(set_to_none=False)
         torch._foreach_lerp_(self.ema, [p.detach() for p in self.params], 1.0 - self.ema_decay)
         return loss.detach(), loss_dict
+
+    # ------------------------------------------------------------------ one CUDA graph per step
+    def _device_step(self, sim_points: torch.Tensor, real_points: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """``step`` without host syncs: loss dictionary as device tensors."""
+        self.loss_fn.sync_items = False
+        try:
+            loss, loss_dict = self.loss(sim_points, real_points)
+        finally:
+            self.loss_fn.sync_items = True
+        loss.backward()
+        average_gradients(self.flat_grad, self.world)
+        torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
+        self.optimizer.step()
+        self.flat_grad.zero_()
+        torch._foreach_lerp_(self.ema, [p.detach() for p in self.params], 1.0 - self.ema_decay)
+        return loss.detach(), loss_dict
+
+    def _capture(self, sim_points: torch.Tensor, real_points: torch.Tensor) -> None:
+        enc = self.model.style_encoder.encoder
+        B = sim_points.shape[0]
+        n1 = min(real_points.shape[1], self.config.global_points) if self.config.use_hierarchical else real_points.shape[1]
+        st = {"sim": sim_points.clone(), "real": real_points.clone(),
+              "starts": torch.zeros(2, B, dtype=torch.long, device=self.device),
+              # pinned staging ring: a slot is rewritten only after its copy has completed (the host runs ahead of replays)
+              "starts_host": [torch.zeros(2, B, dtype=torch.long).pin_memory() for _ in range(8)],
+              "copied": [None] * 8, "slot": 0, "n1": n1}
+        enc.static_starts = (st["starts"][0], st["starts"][1])
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):                      # allocator, lazy initialisations, optimizer state
+                self._draw_starts(st)
+                self._device_step(st["sim"], st["real"])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st["loss"], st["loss_dict"] = self._device_step(st["sim"], st["real"])
+        st["graph"] = g
+        self._graph = st
+
+    def _draw_starts(self, st: dict) -> None:
+        """The reference's two FPS start draws of the style encoder (sa1 on the coarse condition cloud, then sa2), CPU
+        default generator (models/pointnet2_encoder.py:36)."""
+        enc = self.model.style_encoder.encoder
+        slot = st["slot"]
+        st["slot"] = (slot + 1) % len(st["starts_host"])
+        if st["copied"][slot] is not None:
+            st["copied"][slot].synchronize()
+        host = st["starts_host"][slot]
+        torch.randint(0, st["n1"], (host.shape[1],), dtype=torch.long, out=host[0])
+        torch.randint(0, enc.sa1.npoint, (host.shape[1],), dtype=torch.long, out=host[1])
+        st["starts"].copy_(host, non_blocking=True)
+        ev = st["copied"][slot] = st["copied"][slot] or torch.cuda.Event()
+        ev.record()
+
+    def step_graphed(self, sim_points: torch.Tensor, real_points: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """One batch as one CUDA-graph replay.  Returns the graph's static (loss, loss_dict) device tensors (valid until the
+        next call); read them with ``float()`` when a host value is needed."""
+        if self._graph is None or self._graph["sim"].shape != sim_points.shape or self._graph["real"].shape != real_points.shape:
+            self.release()
+            self._capture(sim_points, real_points)
+        st = self._graph
+        if sim_points.data_ptr() != st["sim"].data_ptr():
+            st["sim"].copy_(sim_points, non_blocking=True)
+        if real_points.data_ptr() != st["real"].data_ptr():
+            st["real"].copy_(real_points, non_blocking=True)
+        self._draw_starts(st)
+        st["graph"].replay()
+        return st["loss"], st["loss_dict"]
+
+    def release(self) -> None:
+        """Drop the captured graph (it holds NCCL kernels when world > 1: must go before ``destroy_process_group``)."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.model.style_encoder.encoder.static_starts = None
+            self._graph = None

@@ -843,6 +843,54 @@ def test_training_step_native_kernels_against_torch_backend(api, dev):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
+def test_training_step_as_one_cuda_graph(api, dev):
+    """``DiffusionTrainStep.step_graphed``: forward, backward, clip, AdamW and EMA of one batch as ONE CUDA-graph replay.
+    The random draws (timestep, noise, CFG dropout, voxel thinning) come from the device generator in both modes, so the
+    two modes are compared in distribution: from the same initial weights the graphed steps start at the eager steps'
+    loss level, every replay moves the parameters, BatchNorm's batch counter advances once per step, and 60 steps on a
+    fixed batch do not diverge.  No kernel of the library is launched from Python during a replay."""
+    from pointcloud_style_transfer_b200 import ops
+    from pointcloud_style_transfer_b200.config import Config
+    from pointcloud_style_transfer_b200.train_step import DiffusionTrainStep
+
+    cfg = Config()
+    cfg.total_points, cfg.global_points, cfg.learning_rate = 2048, 512, 1e-3
+    torch.manual_seed(0)
+    a = DiffusionTrainStep(cfg, dev, mlp_precision=1)
+    b = DiffusionTrainStep(cfg, dev, mlp_precision=1)
+    b.model.load_state_dict(a.model.state_dict())
+    sim = torch.cat([S.lidar_scan(0, 2048), S.lidar_scan(1, 2048)], 0).to(dev)
+    real = torch.cat([S.lidar_scan(2, 2048), S.lidar_scan(3, 2048)], 0).to(dev)
+    torch.manual_seed(5)
+    torch.cuda.manual_seed(5)
+    eager = [float(a.step(sim, real)[0]) for _ in range(8)]
+    bn = b.model.style_encoder.encoder.sa1.mlp_bns[0]
+    graphed = []
+    loss, d = b.step_graphed(sim, real)                      # warm-up steps + capture + first replay
+    graphed.append(float(loss))
+    assert set(d) == {"noise_loss", "chamfer_loss", "total_loss"} and all(torch.is_tensor(v) for v in d.values())
+    n0 = int(bn.num_batches_tracked)
+    before = [p.detach().clone() for p in b.params]
+    launches = ops.launch_count
+    for _ in range(59):
+        loss, _ = b.step_graphed(sim, real)
+        graphed.append(float(loss))
+    assert ops.launch_count == launches, "a replay must not launch from Python"
+    assert int(bn.num_batches_tracked) == n0 + 59
+    assert all(np.isfinite(graphed))
+    assert any(not torch.equal(p0, p1) for p0, p1 in zip(before, b.params))
+    assert float(b.flat_grad.abs().max()) == 0.0
+    # same loss level as the eager steps at the start (medians: a draw of t near T makes the x0 prediction of the Chamfer
+    # branch blow up, (noisy - s * pred) / (a + 1e-8) with a ~ 0, in the reference's formulation and here alike), and the
+    # optimisation does not diverge
+    assert 0.5 * np.median(eager) <= np.median(graphed[:8]) <= 2.0 * np.median(eager), (eager, graphed[:8])
+    assert np.median(graphed[-15:]) <= 1.05 * np.median(graphed[:15]), (graphed[:15], graphed[-15:])
+    b.release()
+    assert b.model.style_encoder.encoder.static_starts is None
+    loss, _ = b.step(sim, real)                              # the host-driven step still works after the graph is gone
+    assert torch.isfinite(loss)
+
+
 # ------------------------------------------------------------------------- NoisePredictor (next row, rank 2)
 
 
