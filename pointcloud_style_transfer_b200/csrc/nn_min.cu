@@ -201,7 +201,7 @@ constexpr int kPairStages = 2;  // a 1024-candidate tile is ~50 us of work per C
 template <int FORM>
 __global__ void __launch_bounds__(kNNThreads, 2)
 nn_min_pair_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, int N, int M, int Npad, int Mpad,
-                   int tiles_per_split, unsigned int* __restrict__ rowmin_bits, unsigned int* __restrict__ colmin_bits) {
+                   unsigned int* __restrict__ rowmin_bits, unsigned int* __restrict__ colmin_bits) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);                                         // [stages][1024]
     unsigned int* colw = reinterpret_cast<unsigned int*>(smem_raw + kPairStages * kTileBytes);   // [2][8 warps][1024]
@@ -211,11 +211,17 @@ nn_min_pair_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const int total_tiles = Mpad / kTilePoints;
-    const int tile0 = blockIdx.y * tiles_per_split;
-    int ntiles = total_tiles - tile0;
-    if (ntiles > tiles_per_split) ntiles = tiles_per_split;
-    if (ntiles <= 0) return;  // uniform per CTA
+    // Candidate split blockIdx.y of gridDim.y owns a contiguous range of 32-candidate UNITS, balanced to one unit: the
+    // splits need not be whole 1024-candidate tiles, so the host can pick the split count that fills the machine exactly
+    // (a query shard of 15 000 rows is 8 row tiles: 37 splits = 296 CTAs of 101-102 units; whole-tile splits left 20 % of
+    // the tile slots empty).  Tiles still arrive whole by TMA; the first and last tile of a range are swept partially.
+    const int units_total = Mpad / 32;
+    const int u_lo = (int)(((long long)units_total * blockIdx.y) / gridDim.y);
+    const int u_hi = (int)(((long long)units_total * (blockIdx.y + 1)) / gridDim.y);
+    if (u_hi <= u_lo) return;  // uniform per CTA
+    constexpr int kUnitsPerTile = kTilePoints / 32;
+    const int tile0 = u_lo / kUnitsPerTile;
+    const int ntiles = (u_hi + kUnitsPerTile - 1) / kUnitsPerTile - tile0;
     const float4* cand = Bp + (size_t)b * Mpad + (size_t)tile0 * kTilePoints;
 
     if (tid == 0) {
@@ -273,8 +279,11 @@ nn_min_pair_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, 
         mbar_wait(&full_bar[s], (uint32_t)((t / kPairStages) & 1));
         const float4* tile = tiles + (size_t)s * kTilePoints;
         unsigned int* strip = colw + ((size_t)(t & 1) * kWarps + warp) * kTilePoints;
+        const int ubase = (tile0 + t) * kUnitsPerTile;   // this CTA's part of the tile, in candidates
+        const int jb_lo = (u_lo > ubase ? u_lo - ubase : 0) * 32;
+        const int jb_hi = (u_hi - ubase < kUnitsPerTile ? u_hi - ubase : kUnitsPerTile) * 32;
 #pragma unroll 1
-        for (int jb = 0; jb < kTilePoints; jb += 32) {
+        for (int jb = jb_lo; jb < jb_hi; jb += 32) {
             unsigned int mine = 0x7f800000u;
 #pragma unroll 4
             for (int jj = 0; jj < 32; jj += 2) {
@@ -298,7 +307,7 @@ nn_min_pair_kernel(const float4* __restrict__ A, const float4* __restrict__ Bp, 
         // merge the strips; strips of this parity are rewritten in tile t + 2, after the next __syncthreads
         const unsigned int* base = colw + (size_t)(t & 1) * kWarps * kTilePoints;
         const int jbase = (tile0 + t) * kTilePoints;
-        for (int q = tid; q < kTilePoints; q += kNNThreads) {
+        for (int q = jb_lo + tid; q < jb_hi; q += kNNThreads) {
             unsigned int v = base[q];
 #pragma unroll
             for (int w = 1; w < kWarps; ++w) v = min(v, base[w * kTilePoints + q]);
@@ -550,6 +559,7 @@ __global__ void nn_min_finalize_kernel(float* rowmin, int64_t* rowarg, const uns
 
 struct NNPlan {
     int Npad, Mpad, row_tiles, splits, tiles_per_split, R;
+    int pair_splits;  // candidate splits of nn_min_pair_kernel (unit-balanced)
     size_t off_a, off_b, off_key, total;
 };
 
@@ -582,6 +592,24 @@ static NNPlan make_plan(int B, int N, int M, int R = 4) {
     }
     p.tiles_per_split = (cand_tiles + best_s - 1) / best_s;
     p.splits = (cand_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    {   // nn_min_pair_kernel balances its splits to one 32-candidate unit: any split count is as good as its wave fill
+        const int units = p.Mpad / 32;
+        int bs = 1;
+        double be = -1.0;
+        for (int s = 1; s <= units && s <= 1024; ++s) {
+            if (forced) s = forced < units ? forced : units;
+            const long ctas = (long)p.row_tiles * s * B;
+            const long waves = (ctas + wave - 1) / wave;
+            // per-CTA cost = its units + ~11 units of fixed overhead (row load, atomics, launch tail) + the partial tiles' fetch
+            const double eff = ((double)p.row_tiles * units * B) / ((double)waves * wave * ((double)units / s + 11.0));
+            if (eff > be + 1e-9) {
+                be = eff;
+                bs = s;
+            }
+            if (forced) break;
+        }
+        p.pair_splits = bs;
+    }
     p.off_a = 0;
     p.off_b = align_up(p.off_a + (size_t)B * p.Npad * sizeof(float4), 256);
     p.off_key = align_up(p.off_b + (size_t)B * p.Mpad * sizeof(float4), 256);
@@ -677,17 +705,15 @@ extern "C" int pcst_nn_min_pair_f32(const float* a, const float* b, int B, int N
                                                                                     (unsigned int*)colmin, nb);
     PCST_CUDA(cudaGetLastError());
     const int smem = kPairStages * kTileBytes + 2 * (kNNThreads / 32) * kTilePoints * (int)sizeof(unsigned int);
-    dim3 grid(p.row_tiles, p.splits, B);
+    dim3 grid(p.row_tiles, p.pair_splits, B);
     if (form == 0) {
         auto kern = nn_min_pair_kernel<0>;
         PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<grid, kNNThreads, smem, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, p.tiles_per_split, (unsigned int*)rowmin,
-                                                 (unsigned int*)colmin);
+        kern<<<grid, kNNThreads, smem, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, (unsigned int*)rowmin, (unsigned int*)colmin);
     } else {
         auto kern = nn_min_pair_kernel<1>;
         PCST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<grid, kNNThreads, smem, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, p.tiles_per_split, (unsigned int*)rowmin,
-                                                 (unsigned int*)colmin);
+        kern<<<grid, kNNThreads, smem, stream>>>(A, Bp, N, M, p.Npad, p.Mpad, (unsigned int*)rowmin, (unsigned int*)colmin);
     }
     PCST_CUDA(cudaGetLastError());
     if (form != 0) {
