@@ -120,7 +120,8 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
     // the step table is walked by every role with a run-time index: from shared memory (an indexed read of the kernel
     // parameters is a constant-cache access per field and was measured at ~2 000 cycles per step)
     __shared__ __align__(16) NpStep steps[kNpMaxSteps];
-    __shared__ long long stamp[4][kNpMaxSteps];   // probe 64: issuer commit, epilogue wake, epilogue arrive, issuer wake (per step)
+    __shared__ long long stamp[5][kNpMaxSteps];   // probe 64: issuer commit, epilogue wake, epilogue arrive, issuer wake,
+                                                  // cycles the issuer waited for weight stages (per step)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role branches and their loop
@@ -217,8 +218,15 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
             uint32_t a_lo = (((smem_base + st.a_off) >> 4) & 0x3FFFu) | (((kTcM * 16u) >> 4) << 16);
             uint32_t accum = st.acc;
             const uint32_t nchunks = st.nchunks, nk_full = st.nk, nk_last = st.nk_last;
+            long long waited = 0;
             for (uint32_t c = 0; c < nchunks; ++c) {
-                mbar_wait_addr(full0 + stage * 8u, round & 1u);
+                if (a.probe & 64) {
+                    const long long t0 = clock64();
+                    mbar_wait_addr(full0 + stage * 8u, round & 1u);
+                    waited += clock64() - t0;
+                } else {
+                    mbar_wait_addr(full0 + stage * 8u, round & 1u);
+                }
                 tc_fence_after();
                 const uint32_t nk = c + 1 == nchunks ? nk_last : nk_full;
                 if (leader) {
@@ -242,10 +250,11 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
                 accum = 1;
                 if (++stage == nstages) { stage = 0; ++round; }
             }
-            if (st.epi && leader) {
-                if (a.probe & 64) stamp[0][s] = clock64();
-                umma_commit_addr(acc0 + st.bar * 8u);
+            if ((a.probe & 64) && leader) {
+                stamp[4][s] = waited;
+                stamp[0][s] = clock64();
             }
+            if (st.epi && leader) umma_commit_addr(acc0 + st.bar * 8u);
             __syncwarp();
         }
     } else {
@@ -335,8 +344,8 @@ noise_mlp_kernel(const __grid_constant__ NpArgs a) {
                t_role - t_setup, clock64() - t_role);
     if ((a.probe & 64) && tid == 0 && blockIdx.x == 300)
         for (int s2 = 0; s2 < a.nsteps && s2 < 24; ++s2)
-            printf("step %d epi %d wait_ev %d: issuer woke %lld commit %lld | epilogue woke %lld arrived %lld\n", s2,
-                   (int)steps[s2].epi, (int)steps[s2].wait_ev, stamp[3][s2] - t_setup, stamp[0][s2] - t_setup,
+            printf("step %d epi %d wait_ev %d: issuer woke %lld done %lld (waited for weights %lld) | epilogue woke %lld arrived %lld\n",
+                   s2, (int)steps[s2].epi, (int)steps[s2].wait_ev, stamp[3][s2] - t_setup, stamp[0][s2] - t_setup, stamp[4][s2],
                    stamp[1][s2] - t_setup, stamp[2][s2] - t_setup);
 }
 
