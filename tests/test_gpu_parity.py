@@ -954,6 +954,30 @@ def test_noise_predictor_fused_kernel_against_linear_stack(api, dev, B, N, F, T)
     assert _rel_l2(fused, ref) < 1e-2
 
 
+@pytest.mark.parametrize("knob,values", [("noise.cluster", (2, 4)), ("noise.stages", (2, 3, 5))])
+def test_noise_predictor_kernel_variants_are_bit_identical(api, dev, knob, values):
+    """The opt-in variants of the fused denoiser (weight stages multicast over a 2 / 4-CTA cluster; other depths of the
+    weight ring, the deepest of which reads biases from global memory) perform the same MMAs and epilogues in the same
+    order as the default: same bits.  N is chosen so that the grid is padded to whole clusters (3 tiles per element)."""
+    from pointcloud_style_transfer_b200 import _lib
+
+    torch.manual_seed(4)
+    net = api.dm.NoisePredictor(_noise_cfg(256, 128)).to(dev).eval()
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(3, 300, 3, generator=g).to(dev)
+    t = torch.randint(0, 1000, (3,), generator=g).to(dev)
+    style = torch.randn(3, 256, generator=g).to(dev)
+    with torch.no_grad():
+        base = net(x, t, style).cpu().numpy()
+        for v in values:
+            _lib.set_tuning(knob, v)
+            try:
+                got = net(x, t, style).cpu().numpy()
+            finally:
+                _lib.set_tuning(knob, 0)
+            assert np.array_equal(bits(got), bits(base)), (knob, v)
+
+
 # ------------------------------------------------------------------------------- Chamfer / NN-min
 
 
@@ -968,6 +992,29 @@ def test_chamfer_c1_golden_bit_exact_minima(api, dev, golden):
     np.testing.assert_allclose(cd, g["chamfer_loss"], rtol=1e-5)
     cd100 = api.losses.chamfer_distance_chunked_optimized(p, t, 100).cpu().numpy()
     np.testing.assert_allclose(cd100, g["chamfer_loss_chunk100"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("splits", [1, 7, 37, 300])
+@pytest.mark.parametrize("B,N,M", [(1, 15000, 120000), (2, 3000, 5000), (1, 40, 33)])
+def test_nn_min_pair_is_independent_of_the_candidate_split(api, dev, B, N, M, splits):
+    """The one-sweep kernel gives split blockIdx.y a range of 32-candidate units that need not be whole 1024-candidate
+    tiles (first / last tile swept partially): every split count must give the default's bits, for both directions --
+    including the 15 000-row query shard of the 8-GPU configuration and more splits than units."""
+    from pointcloud_style_transfer_b200 import _lib
+
+    a, b = S.uniform_cloud(31, B, N).to(dev), S.uniform_cloud(32, B, M).to(dev)
+    r0, c0 = api.ops.nn_min_pair(a, b, 0)
+    _lib.set_tuning("nn_min.splits", splits)
+    try:
+        r1, c1 = api.ops.nn_min_pair(a, b, 0)
+    finally:
+        _lib.set_tuning("nn_min.splits", 0)
+    assert np.array_equal(bits(r0.cpu().numpy()), bits(r1.cpu().numpy()))
+    assert np.array_equal(bits(c0.cpu().numpy()), bits(c1.cpu().numpy()))
+    d1, _ = api.ops.nn_min(a, b, 0, False)
+    d2, _ = api.ops.nn_min(b, a, 0, False)
+    assert np.array_equal(bits(r0.cpu().numpy()), bits(d1.cpu().numpy()))
+    assert np.array_equal(bits(c0.cpu().numpy()), bits(d2.cpu().numpy()))
 
 
 @pytest.mark.parametrize("variant", [1, 2])
