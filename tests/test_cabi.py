@@ -88,6 +88,27 @@ def test_shared_mlp_plan_queries_are_host_only(lib):
     assert lib.pcst_sa_mlp_packed_bytes(0, C3(64, 64, 1024), 1, 1) == lib.pcst_sa_mlp_packed_bytes(0, C3(64, 64, 1024), 0, 1)
 
 
+def test_denoiser_plan_queries_are_host_only(lib):
+    """The fused NoisePredictor's step table (csrc/noise_mlp_tc.cu) is host arithmetic: blob size, workspace and the
+    pack's launch count for the reference's configuration (feature_dim 256, time_embed_dim 128, 6 blocks,
+    models/diffusion_model.py:38-61) and the limits of what the kernel takes."""
+    F, T, nb = 256, 128, 6
+    weights = 2 * (16 * 128 + 128 * 256 + 256 * F + nb * 2 * (F * 2 * F) + F * 256 + 256 * 128 + 128 * 16)   # bf16, K padded
+    side = 4 * (F * T + F * F + 3 * F + nb * F + 128 + 256 + nb * 2 * F + 256 + 128 + 16)                  # fp32 vectors
+    n = lib.pcst_noise_predictor_packed_bytes(F, T, nb)
+    assert weights + side <= n <= weights + side + 64 * 1024
+    # 4 point-encoder steps (the 256-wide layer in two N chunks), 8 per block (4 hidden chunks x 2), 4 output steps;
+    # plus the bias / projection copies
+    assert lib.pcst_noise_predictor_pack_launches(F, T, nb) == (4 + 8 * nb + 4) + 5 + nb
+    assert lib.pcst_noise_predictor_workspace_bytes(2, F, nb) >= 2 * (nb + 1) * F * 4
+    for bad in ((250, T, nb), (272, T, nb), (F, 127, nb), (F, T, 9), (8, T, nb)):
+        assert lib.pcst_noise_predictor_packed_bytes(*bad) == 0
+        assert lib.pcst_noise_predictor_pack_launches(*bad) == 0
+    # narrow widths: the hidden layer is one chunk of 2F <= 128 columns (2 steps per block)
+    assert lib.pcst_noise_predictor_pack_launches(64, 32, 2) == (4 + 2 * 2 + 4) + 5 + 2
+    assert lib.pcst_chamfer_shard_payload_floats(120000) == 120000 + 256
+
+
 def test_tuning_knobs(lib):
     _lib.set_tuning("nn_min.splits", 3)
     assert _lib.get_tuning("nn_min.splits") == 3
