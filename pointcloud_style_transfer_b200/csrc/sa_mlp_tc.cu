@@ -73,6 +73,8 @@ struct TcArgs {
     uint32_t off_ring, stage_bytes, nstages, off_ss, off_pool, tmem_cols;
     float* out;                 // [B*S, cout] point-major
     int pool_atomic;            // 0: every group lies inside one tile (plain stores); 1: atomicMax merge
+    int transpose_pool;         // the pooled layer is computed TRANSPOSED (channels on the TMEM lanes, the tile's rows on the
+                                // columns): the max over a group's rows is then a per-thread max over columns
     uint32_t cluster;           // CTAs per row tile (N split); 1 = no cluster
     unsigned long long* probe;  // profiling aid (pcst_sa_mlp_set_probe): [probe_tiles][16] SM-clock stamps per tile, or null
     int probe_tiles;
@@ -259,6 +261,10 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                 const uint32_t w_lbo = n << 16;                // LBO = n * 16 bytes
                 uint32_t a_lo = (((smem_base + st.a_off) >> 4) & 0x3FFFu) | (((kTcM * 16u) >> 4) << 16);
                 uint32_t accum = st.acc;
+                // pooled layer, transposed: D^T[channel block of 128][the tile's 128 rows] = W[block, :] x A^T -- the
+                // weights are the M-side operand (rows cb * 128 ... of every K group), the activations the N-side one
+                const bool transposed = a.transpose_pool && st.epi != 1;
+                const uint32_t idesc_t = umma_idesc_bf16(kTcM, kTcM);
                 for (uint32_t k0 = 0; k0 < kp; k0 += ckf) {
                     mbar_wait_addr(full0 + stage * 8u, round & 1u);
                     tc_fence_after();
@@ -269,7 +275,12 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                             umma_bf16(d_addr, ((uint64_t)desc_hi << 32) | (a_lo + kk * a_step),
                                       ((uint64_t)desc_hi << 32) | (w_lo + kk * w_step), idesc, acc);
                         };
-                        if (nk == 4) {
+                        if (transposed) {
+                            for (uint32_t kk = 0; kk < nk; ++kk)
+                                for (uint32_t cb = 0; cb < (n >> 7); ++cb)
+                                    umma_bf16(d_addr + cb * 128u, ((uint64_t)desc_hi << 32) | (w_lo + kk * w_step + cb * 128u),
+                                              ((uint64_t)desc_hi << 32) | (a_lo + kk * a_step), idesc_t, (accum | kk) != 0);
+                        } else if (nk == 4) {
                             mma(0, accum != 0); mma(1, true); mma(2, true); mma(3, true);
                         } else if (nk == 2) {
                             mma(0, accum != 0); mma(1, true);
@@ -446,7 +457,36 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                     // ---- max over each group's K rows ----
                     const int row = row0 + m;
                     const bool valid = row < a.rows;
-                    if (!a.pool_atomic) {
+                    if (a.transpose_pool) {
+                        // This thread's TMEM lane is a CHANNEL, the accumulator's 128 columns are the tile's rows: scale /
+                        // shift are two scalars, the max over a group is a running max over its K columns (no warp
+                        // reductions, no staging buffer, no block barrier), and a warp stores 32 consecutive channels of a
+                        // pooled row.  relu(max) == max(relu): the ReLU is applied once per pooled value.
+                        const int rows_here = a.rows - row0 < kTcM ? a.rows - row0 : kTcM;   // valid rows = valid columns
+                        const int g0 = row0 / a.K;                                           // first group of the tile
+                        auto pooled_t = [&](auto masked) {
+                            for (int cb = 0; cb < st.n / 128; ++cb) {
+                                const int ch = cb * 128 + m;
+                                const float scl = sc[ch], sft = sh[ch];
+                                float mx = __int_as_float(0xff800000);
+                                tmem_for_each16(taddr + (uint32_t)cb * 128u, kTcM, [&](const uint32_t (&r)[16], int c0) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        const float y = __fmaf_rn(__uint_as_float(r[i]), scl, sft);
+                                        if (!decltype(masked)::value || c0 + i < rows_here) mx = fmaxf(mx, y);
+                                    }
+                                    if (((c0 + 16) % a.K) == 0) {   // the last 16 rows of a group (K is 32, 64 or 128)
+                                        const int g = g0 + (c0 + 16) / a.K - 1;
+                                        if ((size_t)g * a.K < (size_t)a.rows)
+                                            a.out[(size_t)g * a.cout + st.out_c0 + slice0 + ch] = fmaxf(mx, 0.f);
+                                        mx = __int_as_float(0xff800000);
+                                    }
+                                });
+                            }
+                        };
+                        if (row0 + kTcM <= a.rows) pooled_t(std::false_type{});
+                        else pooled_t(std::true_type{});
+                    } else if (!a.pool_atomic) {
                         // K in {32, 64, 128}: the warp's 32 rows belong to one group and every group lies in this tile
                         float* pool = reinterpret_cast<float*>(smem + a.off_pool);  // [4 warps][n]
                         // relu(max over rows) == max over rows of relu: the warp reduces the RAW scale/shift results as
@@ -764,6 +804,12 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     a.out = out;
     a.pool_atomic = !(K == 32 || K == 64 || K == 128);
     a.cluster = (uint32_t)C;
+    {   // layer-2 steps (the ones that are not operand-writing) all have the same per-CTA width
+        int n2c = 0;
+        for (int s = 0; s < p.nsteps; ++s)
+            if (p.st[s].epi == 2) n2c = p.st[s].n;
+        a.transpose_pool = !a.pool_atomic && n2c > 0 && (n2c % 128) == 0 && tuning("sa_mlp.transpose_pool", 0) != 2;
+    }
     if (a.pool_atomic) PCST_CUDA(cudaMemsetAsync(out, 0, (size_t)B * S * cout[2] * sizeof(float), stream));
     const int tiles = (a.rows + kTcM - 1) / kTcM;
     // the narrow build pays off when tiles queue up on every SM and the stage's shared memory allows three or four CTAs
