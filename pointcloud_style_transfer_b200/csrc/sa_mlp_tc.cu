@@ -276,10 +276,18 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                                       ((uint64_t)desc_hi << 32) | (w_lo + kk * w_step), idesc, acc);
                         };
                         if (transposed) {
-                            for (uint32_t kk = 0; kk < nk; ++kk)
-                                for (uint32_t cb = 0; cb < (n >> 7); ++cb)
-                                    umma_bf16(d_addr + cb * 128u, ((uint64_t)desc_hi << 32) | (w_lo + kk * w_step + cb * 128u),
-                                              ((uint64_t)desc_hi << 32) | (a_lo + kk * a_step), idesc_t, (accum | kk) != 0);
+                            auto mma_t = [&](uint32_t kk, uint32_t cb, bool acc) {
+                                umma_bf16(d_addr + cb * 128u, ((uint64_t)desc_hi << 32) | (w_lo + kk * w_step + cb * 128u),
+                                          ((uint64_t)desc_hi << 32) | (a_lo + kk * a_step), idesc_t, acc);
+                            };
+                            if (n == 256 && nk == 2) {
+                                mma_t(0, 0, accum != 0); mma_t(0, 1, accum != 0); mma_t(1, 0, true); mma_t(1, 1, true);
+                            } else if (n == 128 && nk == 4) {
+                                mma_t(0, 0, accum != 0); mma_t(1, 0, true); mma_t(2, 0, true); mma_t(3, 0, true);
+                            } else {
+                                for (uint32_t kk = 0; kk < nk; ++kk)
+                                    for (uint32_t cb = 0; cb < (n >> 7); ++cb) mma_t(kk, cb, (accum | kk) != 0);
+                            }
                         } else if (nk == 4) {
                             mma(0, accum != 0); mma(1, true); mma(2, true); mma(3, true);
                         } else if (nk == 2) {
@@ -315,6 +323,10 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
         const uint32_t taddr_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
         const int m = tid;  // this thread's row = its TMEM lane
         uint32_t mma_phase = 0, xev = 0;
+        // The gather is a chain of dependent loads (index -> feature row); when a CTA walks several tiles the NEXT tile's
+        // index is requested before this tile's epilogues, so that the chain of the next gather starts one latency shorter.
+        long long idx_next = 0;
+        if (kWalk && a.idx && tile_first * kTcM + tid < a.rows) idx_next = a.idx[tile_first * kTcM + tid];
         for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
             const int row0 = tile * kTcM;
             // stamps: 0 tile start, then per epilogue-bearing step (accumulator ready, epilogue done); 15 = SM id
@@ -340,7 +352,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                 if (valid) {
                     bs = row / a.K;
                     if (a.idx) {
-                        const int64_t jj = a.idx[row];
+                        const int64_t jj = kWalk ? idx_next : a.idx[row];
                         j = jj < 0 ? 0 : (jj >= a.N ? a.N - 1 : (int)jj);
                     } else {
                         j = row % a.K;  // group_all: row k of cloud b is point k
@@ -392,6 +404,10 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                     else if (k - D < 3) v = (k - D) == 0 ? rel[0] : ((k - D) == 1 ? rel[1] : rel[2]);
                     A0[((size_t)(k >> 3) * kTcM + tid) * 8 + (k & 7)] = __float2bfloat16_rn(v);
                 }
+            }
+            if (kWalk && a.idx) {
+                const long long rn = (long long)(tile + tile_stride) * kTcM + tid;
+                if (tile + tile_stride < a.ntiles && rn < a.rows) idx_next = a.idx[rn];
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             if (tile == tile_first) epi_bar_sync();  // the scale/shift tables are complete for every epilogue thread
@@ -623,7 +639,17 @@ struct TcPlan {
 // C = CTAs per row tile (N split over a cluster): every step computes n / C channels per CTA.
 // dense = many more row tiles than SMs: a small weight ring (2 stages of 8 KiB) so that 2-4 CTAs share an SM and one
 // tile's epilogue overlaps another's MMAs; otherwise a deep ring for the latency of a single tile.
-static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false) {
+static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false, int dense_stage_bytes = 0) {
+    if (dense && dense_stage_bytes == 0) {
+        // Stage size of the dense (many tiles per SM) plan: every stage costs the issuer a barrier wait, a commit and ~300
+        // cycles of loop overhead, so take 16 KiB stages when they leave as many CTAs per SM as 8 KiB ones do.
+        const TcPlan small = tc_plan(D, cout, C, true, kTcStageBytes / 2), big = tc_plan(D, cout, C, true, kTcStageBytes);
+        auto per_sm = [](const TcPlan& q) {
+            const uint32_t n = 228u * 1024u / (q.smem_bytes + 1024u);
+            return n < 4u ? n : 4u;
+        };
+        return (big.ok && (!small.ok || per_sm(big) >= per_sm(small))) ? big : small;
+    }
     TcPlan p = {};
     p.ok = false;
     p.C = C;
@@ -662,7 +688,7 @@ static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false) {
     const int max_nc = n0c > n1c ? (n0c > n2c ? n0c : n2c) : (n1c > n2c ? n1c : n2c);
     // K rows per chunk of a step: as many as fit a ring stage (narrow per-CTA slices get long chunks, so that the
     // number of dependent TMA round trips stays small)
-    const int stage_target = dense ? kTcStageBytes / 2 : kTcStageBytes;
+    const int stage_target = dense ? dense_stage_bytes : kTcStageBytes;
     auto chunk_rows = [stage_target](int kp, int nc) {
         int ck = stage_target / (nc * 2) / 16 * 16;
         if (ck < 16) ck = 16;
