@@ -142,6 +142,8 @@ size_t pcst_sa_mlp_packed_bytes(int D, const int* cout /*[3]*/, int precision, i
 int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision, int cluster, void* packed, size_t packed_bytes,
                          pcst_stream_t stream);
 size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision);
+/* __global__ launches of one pcst_sa_mlp_max_f32 call with these sizes (bookkeeping for launch counts; 0 = bad sizes) */
+int pcst_sa_mlp_max_kernel_launches(int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision);
 int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx,
                         int B, int N, int S, int K, int D, const int* cout /*[3]*/, int precision, int cluster,
                         const void* packed, float* out, void* ws, size_t ws_bytes, pcst_stream_t stream);

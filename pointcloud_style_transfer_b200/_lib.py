@@ -75,6 +75,7 @@ SIGNATURES = {
     "pcst_sa_mlp_packed_bytes": (c_size_t, [c_int, POINTER(c_int), c_int, c_int]),
     "pcst_sa_mlp_pack_f32": (c_int, [POINTER(Mlp3), c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pcst_sa_mlp_max_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int]),
+    "pcst_sa_mlp_max_kernel_launches": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int]),
     "pcst_sa_mlp_max_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     POINTER(c_int), c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pcst_sa_mlp_train_saved_bytes": (c_size_t, [c_int, c_int, c_int, c_int, POINTER(c_int)]),

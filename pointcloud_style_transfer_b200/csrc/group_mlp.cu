@@ -156,7 +156,10 @@ int sa_mlp_tc_pick_cluster(long tiles, int D, const int* cout);
 size_t sa_mlp_tc_blob_bytes(int D, const int* cout, int C);
 int sa_mlp_tc_pack(const pcst_mlp3_t* mlp, int D, int C, void* blob, cudaStream_t stream);
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
-                  int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream);
+                  int K, int D, const int* cout, int C, const void* blob, float* out, void* ws, size_t ws_bytes,
+                  cudaStream_t stream);
+size_t sa_mlp_tc_workspace_bytes(int B, int N, int S, int K, int D);
+int sa_mlp_tc_launches(int B, int N, int S, int K, int D);
 void sa_mlp_tc_set_probe(unsigned long long* buf, int tiles);
 
 // fp32 blob: w0 [n0, 3+D] | w1 [n1, n0] | w2 [n2, n1] | scale0 shift0 scale1 shift1 scale2 shift2, each 256-byte aligned
@@ -233,9 +236,15 @@ extern "C" int pcst_sa_mlp_pack_f32(const pcst_mlp3_t* mlp, int D, int precision
 
 extern "C" size_t pcst_sa_mlp_max_workspace_bytes(int B, int N, int S, int K, int D, const int* cout, int precision) {
     if (B <= 0 || N <= 0 || S <= 0 || K <= 0 || D < 0 || !check_cout(cout)) return 0;
-    if (use_tc(D, cout, precision)) return 0;  // activations stay in shared memory / TMEM
+    if (use_tc(D, cout, precision)) return sa_mlp_tc_workspace_bytes(B, N, S, K, D);  // activations stay in shared memory /
+                                                                                      // TMEM; a bf16 copy of feats at throughput shapes
     const size_t rows = (size_t)B * S * K;
     return align_up(rows * cout[0] * sizeof(float), 256) + align_up(rows * cout[1] * sizeof(float), 256);
+}
+
+extern "C" int pcst_sa_mlp_max_kernel_launches(int B, int N, int S, int K, int D, const int* cout, int precision) {
+    if (B <= 0 || N <= 0 || S <= 0 || K <= 0 || D < 0 || !check_cout(cout)) return 0;
+    return use_tc(D, cout, precision) ? sa_mlp_tc_launches(B, N, S, K, D) : 3;
 }
 
 extern "C" void pcst_sa_mlp_set_probe(unsigned long long* stamps, int tiles) { pcst::sa_mlp_tc_set_probe(stamps, tiles); }
@@ -253,7 +262,7 @@ int pcst_sa_mlp_max_f32(const float* xyz, const float* feats, const float* new_x
     PCST_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16 tensor cores)");
     PCST_CHECK_ARG(((uintptr_t)packed & 255) == 0, "packed must be 256-byte aligned");
     if (use_tc(D, cout, precision))
-        return sa_mlp_tc_run(xyz, feats, new_xyz, idx, B, N, S, K, D, cout, cluster, packed, out, stream);
+        return sa_mlp_tc_run(xyz, feats, new_xyz, idx, B, N, S, K, D, cout, cluster, packed, out, ws, ws_bytes, stream);
 
     const size_t need = pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, cout, precision);
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 255)) {

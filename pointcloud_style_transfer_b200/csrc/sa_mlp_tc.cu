@@ -62,6 +62,8 @@ struct TcStep {
 struct TcArgs {
     const float* xyz;
     const float* feats;
+    const __nv_bfloat16* feats_bf16;  // optional bf16 copy of feats (same rounding as the gather's own conversion): half the
+                                      // bytes and half the loads of the gather; made per call at throughput shapes
     const float* new_xyz;
     const int64_t* idx;
     int N, S, K, D, rows;
@@ -104,6 +106,17 @@ __global__ void tc_pack_ss_kernel(const float* __restrict__ scale, const float* 
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
         out[at + c] = scale[c];
         out[total_ch + at + c] = shift[c];
+    }
+}
+
+// fp32 feature rows -> bf16 (round to nearest even, exactly what the gather does per element), 8 channels per thread
+__global__ void tc_feats_to_bf16_kernel(const float* __restrict__ in, uint4* __restrict__ out, size_t n8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+        out[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                            *reinterpret_cast<uint32_t*>(&h3));
     }
 }
 
@@ -371,7 +384,23 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                 const float* frow = D > 0 ? a.feats + ((size_t)b * a.N + j) * D : nullptr;
                 const bool vec = D > 0 && (D % 8) == 0 && ((reinterpret_cast<uintptr_t>(a.feats) & 15) == 0);
                 int kdone = 0;
-                if (vec) {
+                if (a.feats_bf16) {
+                    // bf16 rows (the host guarantees D % 8 == 0): 16 bytes = one K group, stored as loaded
+                    const uint4* frow16 = reinterpret_cast<const uint4*>(a.feats_bf16 + ((size_t)b * a.N + j) * D);
+                    const int G = D / 8;
+                    for (int g0 = 0; g0 < G; g0 += 16) {
+                        uint4 v[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            v[u] = make_uint4(0u, 0u, 0u, 0u);
+                            if (valid && g0 + u < G) v[u] = __ldg(frow16 + g0 + u);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u)
+                            if (g0 + u < G) *reinterpret_cast<uint4*>(A0b + ((size_t)(g0 + u) * kTcM + tid) * 16) = v[u];
+                    }
+                    kdone = D;
+                } else if (vec) {
                     const int G = D / 8;
                     for (int g0 = 0; g0 < G; g0 += 8) {
                         float4 v[16];
@@ -805,8 +834,20 @@ void sa_mlp_tc_set_probe(unsigned long long* buf, int tiles) {
     g_tc_probe_tiles = buf ? tiles : 0;
 }
 
+// bf16 copy of the feature tensor: worth its extra launch when every feature row is gathered many times and the launch is
+// not on a latency-critical path (many more row tiles than SMs)
+static bool tc_wants_bf16_feats(size_t rows, int B, int N, int D) {
+    return D >= 32 && (D % 8) == 0 && (rows + kTcM - 1) / kTcM > (size_t)2 * num_sms() && rows >= (size_t)4 * B * N &&
+           tuning("sa_mlp.bf16_feats", 0) != 2;
+}
+size_t sa_mlp_tc_workspace_bytes(int B, int N, int S, int K, int D) {
+    return tc_wants_bf16_feats((size_t)B * S * K, B, N, D) ? align_up((size_t)B * N * D * 2, 256) : 0;
+}
+int sa_mlp_tc_launches(int B, int N, int S, int K, int D) { return tc_wants_bf16_feats((size_t)B * S * K, B, N, D) ? 2 : 1; }
+
 int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, const int64_t* idx, int B, int N, int S,
-                  int K, int D, const int* cout, int C, const void* blob, float* out, cudaStream_t stream) {
+                  int K, int D, const int* cout, int C, const void* blob, float* out, void* ws, size_t ws_bytes,
+                  cudaStream_t stream) {
     const size_t rows_sz = (size_t)B * S * K;
     const TcPlan p = tc_plan(D, cout, C, /*dense=*/(rows_sz + kTcM - 1) / kTcM > (size_t)2 * num_sms());
     if (!p.ok) {
@@ -820,6 +861,16 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     TcArgs a = {};
     a.xyz = xyz; a.feats = feats; a.new_xyz = new_xyz; a.idx = idx;
     a.N = N; a.S = S; a.K = K; a.D = D; a.rows = (int)rows_sz;
+    a.feats_bf16 = nullptr;
+    if (feats && ws && ((uintptr_t)ws & 255) == 0 && ((uintptr_t)feats & 15) == 0 && tc_wants_bf16_feats(rows_sz, B, N, D) &&
+        ws_bytes >= sa_mlp_tc_workspace_bytes(B, N, S, K, D)) {
+        const size_t n8 = (size_t)B * N * D / 8;
+        unsigned blocks = (unsigned)((n8 + 255) / 256);
+        if (blocks > 8u * (unsigned)num_sms()) blocks = 8u * (unsigned)num_sms();
+        tc_feats_to_bf16_kernel<<<blocks, 256, 0, stream>>>(feats, (uint4*)ws, n8);
+        PCST_CUDA(cudaGetLastError());
+        a.feats_bf16 = (const __nv_bfloat16*)ws;
+    }
     a.blob = (const unsigned char*)blob;
     a.ss_blob_off = p.ss_blob_off;
     a.total_ch = p.total_ch; a.kp0 = p.kp0; a.cout = cout[2];

@@ -337,7 +337,8 @@ def sa_mlp_max(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], 
         nb = lib.pcst_sa_mlp_max_workspace_bytes(B, N, S, K, D, c3, precision)
         ws = _workspace(nb, xyz.device)
         _call("pcst_sa_mlp_max_f32", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, D, c3, precision, cluster,
-              _p(packed), _p(out), _p(ws), ws.numel(), _stream(), kernels=1 if nb == 0 else 3)
+              _p(packed), _p(out), _p(ws), ws.numel(), _stream(),
+              kernels=int(lib.pcst_sa_mlp_max_kernel_launches(B, N, S, K, D, c3, precision)))
     return out
 
 
