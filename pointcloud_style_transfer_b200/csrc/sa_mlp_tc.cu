@@ -427,6 +427,16 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                     }
                     kdone = D;
                 }
+                if (kdone == D && (D % 8) == 0) {
+                    // the tail starts on a K-group boundary: (rel x, rel y, rel z, 0 ...) and zero groups, one 16-byte store each
+                    // (element-wise 2-byte stores of a warp land 8 to a bank)
+                    __nv_bfloat162 xy = __floats2bfloat162_rn(rel[0], rel[1]), z0 = __floats2bfloat162_rn(rel[2], 0.f);
+                    *reinterpret_cast<uint4*>(A0b + ((size_t)(D >> 3) * kTcM + tid) * 16) =
+                        make_uint4(*reinterpret_cast<uint32_t*>(&xy), *reinterpret_cast<uint32_t*>(&z0), 0u, 0u);
+                    for (int g = (D >> 3) + 1; g < (kp0 >> 3); ++g)
+                        *reinterpret_cast<uint4*>(A0b + ((size_t)g * kTcM + tid) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    kdone = kp0;
+                }
                 for (int k = kdone; k < kp0; ++k) {  // feature tail (unaligned D), relative coordinates, zero padding
                     float v = 0.f;
                     if (k < D) v = valid ? __ldg(frow + k) : 0.f;
