@@ -51,6 +51,8 @@ static std::map<std::string, int>& tune_map() {
         {"fps.lookahead", 0},         // 0/2 = one sample per exchange (default); 1 = exact two-sample look-ahead kernel; 3, 4 = its probes
         {"knn.grid", 0},              // 0 = auto, 1 = always the exact grid search, 2 = always the brute-force sweep
         {"noise.cluster", 0},         // 0 / 1 = off, 2 / 4 = CTAs per cluster sharing the denoiser's weight stages by TMA multicast
+        {"sa_mlp.reuse_h", 0},        // 0/1 = layer 1's output overwrites layer 0's in shared memory (plain one-CTA plans), 2 = off
+        {"sa_mlp.early_gather", 0},   // 0/1 = the next row tile is gathered under the current tile's last MMAs (walk build), 2 = off
         {"sa_mlp.bf16_feats", 0},     // 0/1 = bf16 copy of the feature tensor for the gather at throughput shapes, 2 = off
         {"sa_mlp.transpose_pool", 0}, // 0/1 = pooled layer computed transposed (per-thread max over the rows), 2 = row-major + warp reductions
         {"noise.stages", 0},          // weight-ring stages of the denoiser kernel (0 = as many as fit beside the staged bias vectors: 4)

@@ -75,6 +75,7 @@ struct TcArgs {
     uint32_t off_ring, stage_bytes, nstages, off_ss, off_pool, tmem_cols;
     float* out;                 // [B*S, cout] point-major
     int pool_atomic;            // 0: every group lies inside one tile (plain stores); 1: atomicMax merge
+    int early_gather;           // plain three-step plan whose layer-1 output overwrites layer 0's: the next tile is gathered early
     int transpose_pool;         // the pooled layer is computed TRANSPOSED (channels on the TMEM lanes, the tile's rows on the
                                 // columns): the max over a group's rows is then a per-thread max over columns
     uint32_t cluster;           // CTAs per row tile (N split); 1 = no cluster
@@ -340,17 +341,8 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
         // index is requested before this tile's epilogues, so that the chain of the next gather starts one latency shorter.
         long long idx_next = 0;
         if (kWalk && a.idx && tile_first * kTcM + tid < a.rows) idx_next = a.idx[tile_first * kTcM + tid];
-        for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
-            const int row0 = tile * kTcM;
-            // stamps: 0 tile start, then per epilogue-bearing step (accumulator ready, epilogue done); 15 = SM id
-            unsigned long long* stamp = (kWalk && a.probe && tid == 0 && rank == 0 && tile < a.probe_tiles) ? a.probe + (size_t)tile * 16 : nullptr;
-            int nstamp = 0;
-            if (stamp) {
-                uint32_t smid;
-                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                stamp[15] = smid;
-                stamp[nstamp++] = clock64();
-            }
+        // gather of row tile gt into the layer-0 operand buffer (tiles are gathered in walk order: idx_next is gt's index)
+        auto gather_tile = [&](int gt) {
             {
                 // Layer-0 operand, one thread per row: operand row k = feature channel k (k < D), then the three
                 // relative coordinates, then zero padding up to kp0.  Features are read with 16 independent 128-bit
@@ -359,7 +351,7 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                 unsigned char* A0b = smem + a.st[0].a_off;
                 __nv_bfloat16* A0 = reinterpret_cast<__nv_bfloat16*>(A0b);
                 const int D = a.D, kp0 = a.kp0;
-                const int row = row0 + tid;
+                const int row = gt * kTcM + tid;
                 const bool valid = row < a.rows;
                 int j = 0, bs = 0;
                 if (valid) {
@@ -445,9 +437,24 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
                 }
             }
             if (kWalk && a.idx) {
-                const long long rn = (long long)(tile + tile_stride) * kTcM + tid;
-                if (tile + tile_stride < a.ntiles && rn < a.rows) idx_next = a.idx[rn];
+                const long long rn = (long long)(gt + tile_stride) * kTcM + tid;
+                if (gt + tile_stride < a.ntiles && rn < a.rows) idx_next = a.idx[rn];
             }
+        };
+        bool gathered = false;  // the tile's operand is already in place (gathered under the previous tile's last MMAs)
+        for (int tile = tile_first; tile < a.ntiles; tile += kWalk ? tile_stride : a.ntiles) {
+            const int row0 = tile * kTcM;
+            // stamps: 0 tile start, then per epilogue-bearing step (accumulator ready, epilogue done); 15 = SM id
+            unsigned long long* stamp = (kWalk && a.probe && tid == 0 && rank == 0 && tile < a.probe_tiles) ? a.probe + (size_t)tile * 16 : nullptr;
+            int nstamp = 0;
+            if (stamp) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                stamp[15] = smid;
+                stamp[nstamp++] = clock64();
+            }
+            if (!gathered) gather_tile(tile);
+            gathered = false;
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             if (tile == tile_first) epi_bar_sync();  // the scale/shift tables are complete for every epilogue thread
             tc_fence_before();    // (later tiles) the previous tile's accumulator reads precede the MMAs this releases
@@ -457,6 +464,13 @@ sa_mlp_tc_kernel(const __grid_constant__ TcArgs a) {
             for (int s = 0; s < a.nsteps; ++s) {
                 const TcStep& st = a.st[s];
                 if (!st.epi) continue;
+                if (kWalk && a.early_gather && s == a.nsteps - 1 && tile + tile_stride < a.ntiles) {
+                    // The layer-0 operand buffer has been free since the first step's MMAs (layer 1 writes its output over
+                    // layer 0's, not into it): gather the NEXT tile now, under this tile's last MMAs, instead of after its
+                    // pooled epilogue.  The arrival that publishes it stays at the top of the next iteration.
+                    gather_tile(tile + tile_stride);
+                    gathered = true;
+                }
                 mbar_wait_addr(mma_bar_a, mma_phase & 1u);  // all C CTAs have finished the MMAs up to this step
                 ++mma_phase;
                 tc_fence_after();
@@ -666,7 +680,7 @@ struct TcBlock {
     uint32_t w_off, sub_bytes;          // blob offset of rank 0's sub-block; bytes between ranks' sub-blocks
 };
 struct TcPlan {
-    bool ok;
+    bool ok, reuse_h;
     int nsteps, nblocks, kp0, total_ch, C;
     int n[3];
     TcStep st[kTcMaxSteps];
@@ -742,8 +756,14 @@ static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false, int den
         }
         p.stage_bytes = (uint32_t)align_up(p.stage_bytes, 128);
     }
-    const uint32_t size_x = (uint32_t)kTcM * (p.kp0 > n1h ? p.kp0 : n1h) * 2;  // layer-0 input, later a layer-1 half
-    const uint32_t size_h = (uint32_t)kTcM * n0 * 2;                             // layer-0 output
+    // Plain plans of one CTA per tile (no N / K halves, no cluster): layer 1's output OVERWRITES layer 0's (its readers, the
+    // layer-1 MMAs, are complete when that epilogue starts), so the layer-0 input buffer is free from the first step's
+    // MMAs on and the next tile can be gathered into it early.  Otherwise layer 1's (half) output goes to the input buffer.
+    // Only where there are feature rows to gather (D > 0): the coordinates-only first stage runs 19 % SLOWER with the shared
+    // buffer (measured: 64.7 -> 76.8 us at 32 x 16 384 points) and has next to nothing to gather early.
+    p.reuse_h = (h1 * h2 == 1) && C == 1 && D > 0 && tuning("sa_mlp.reuse_h", 0) != 2;
+    const uint32_t size_x = (uint32_t)kTcM * (p.reuse_h ? p.kp0 : (p.kp0 > n1h ? p.kp0 : n1h)) * 2;  // layer-0 input (later a layer-1 half)
+    const uint32_t size_h = (uint32_t)kTcM * (p.reuse_h ? (n0 > n1 ? n0 : n1) : n0) * 2;               // layer-0 output
     const uint32_t size_ss = (uint32_t)align_up((size_t)2 * p.total_ch * sizeof(float), 128);
     const uint32_t size_pool = (uint32_t)align_up((size_t)4 * n2c * sizeof(float), 128);
     const uint32_t fixed = size_x + size_h + size_ss + size_pool;
@@ -784,8 +804,8 @@ static TcPlan tc_plan(int D, const int* cout, int C, bool dense = false, int den
     for (int fh = 0; fh < h2; ++fh)
         for (int kh = 0; kh < h1; ++kh) {
             // the layer-1 half's output lands in buffer X at K offset 0 (it is the whole K range of the next step)
-            add_step(off_h, off_x, b1[kh], n0, n1c, l1col, 0, n0 + kh * n1h, 0, 1);
-            add_step(off_x, 0, b2[kh][fh], n1h, n2c, 0, fh * n2h, n0 + n1 + fh * n2h, kh > 0, kh == h1 - 1 ? 2 : 0);
+            add_step(off_h, p.reuse_h ? off_h : off_x, b1[kh], n0, n1c, l1col, 0, n0 + kh * n1h, 0, 1);
+            add_step(p.reuse_h ? off_h : off_x, 0, b2[kh][fh], n1h, n2c, 0, fh * n2h, n0 + n1 + fh * n2h, kh > 0, kh == h1 - 1 ? 2 : 0);
         }
     const int cols = (split ? l1col + n1c : 0) > max_nc ? l1col + n1c : max_nc;
     p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
@@ -891,6 +911,7 @@ int sa_mlp_tc_run(const float* xyz, const float* feats, const float* new_xyz, co
     a.out = out;
     a.pool_atomic = !(K == 32 || K == 64 || K == 128);
     a.cluster = (uint32_t)C;
+    a.early_gather = p.reuse_h && p.nsteps == 3 && tuning("sa_mlp.early_gather", 0) != 2;
     {   // layer-2 steps (the ones that are not operand-writing) all have the same per-CTA width
         int n2c = 0;
         for (int s = 0; s < p.nsteps; ++s)
