@@ -302,6 +302,9 @@ typedef struct {
 size_t pcst_noise_predictor_packed_bytes(int feature_dim, int time_dim, int nblocks);
 /* __global__ launches of one pcst_noise_predictor_pack_f32 call (0 = unsupported sizes); bookkeeping for launch counts */
 int pcst_noise_predictor_pack_launches(int feature_dim, int time_dim, int nblocks);
+/* Host-only consistency check of the kernel's step table for these sizes (dependencies between MMA steps and epilogues, buffer
+ * ranges): 0 = consistent, -1 = unsupported sizes, > 0 = the violated rule (csrc/noise_mlp_tc.cu).  Test aid. */
+int pcst_noise_predictor_plan_selfcheck(int feature_dim, int time_dim, int nblocks);
 size_t pcst_noise_predictor_workspace_bytes(int B, int feature_dim, int nblocks);
 int pcst_noise_predictor_pack_f32(const pcst_noise_mlp_t* mlp, void* packed, size_t packed_bytes, pcst_stream_t stream);
 int pcst_noise_predictor_f32(const float* points, const int64_t* timestep, const float* style, int B, int N, int feature_dim,

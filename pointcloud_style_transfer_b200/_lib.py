@@ -88,6 +88,7 @@ SIGNATURES = {
                                          c_void_p, c_size_t, c_void_p]),
     "pcst_noise_predictor_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_noise_predictor_pack_launches": (c_int, [c_int, c_int, c_int]),
+    "pcst_noise_predictor_plan_selfcheck": (c_int, [c_int, c_int, c_int]),
     "pcst_noise_predictor_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcst_noise_predictor_pack_f32": (c_int, [POINTER(NoiseMlp), c_void_p, c_size_t, c_void_p]),
     "pcst_noise_predictor_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

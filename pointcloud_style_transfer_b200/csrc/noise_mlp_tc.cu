@@ -547,6 +547,44 @@ extern "C" int pcst_noise_predictor_pack_launches(int feature_dim, int time_dim,
     const NpPlan p = np_plan(feature_dim, time_dim, nblocks);
     return p.ok ? p.pack_launches : 0;
 }
+// Host-side self-check of the step table (no GPU): the schedule's invariants for ANY supported (feature_dim, blocks), also the
+// ones no GPU test runs.  0 = consistent; otherwise the number of the first violated rule:
+//   1 a step waits for an event that no earlier step produces (deadlock)        2 wait counts decrease
+//   3 two events on the same barrier could both complete before the issuer has seen the first (parity ambiguity)
+//   4 a step may read its operand before the epilogue that writes it has finished (RAW)
+//   5 a step may overwrite accumulator columns an earlier epilogue still reads (WAR)
+//   6 an operand / accumulator range leaves its buffer                           7 the chain does not end in the output step
+extern "C" int pcst_noise_predictor_plan_selfcheck(int feature_dim, int time_dim, int nblocks) {
+    const NpPlan p = np_plan(feature_dim, time_dim, nblocks);
+    if (!p.ok) return -1;
+    int produced = 1;   // event 0 = the input operand
+    int prev_wait = 0;
+    struct W { uint32_t lo, hi; int ev; };
+    W writes[kNpMaxSteps + 1]; int nw = 0;
+    W reads[kNpMaxSteps + 1]; int nr = 0;
+    writes[nw++] = {p.off_x, p.off_x + 2u * kTcM * 16u, 0};
+    for (int s = 0; s < p.nsteps; ++s) {
+        const NpStep& st = p.st[s];
+        if ((int)st.wait_ev > produced) return 1;
+        if ((int)st.wait_ev < prev_wait) return 2;
+        prev_wait = st.wait_ev;
+        const uint32_t alo = st.a_off, ahi = st.a_off + (uint32_t)st.kp * kTcM * 2u;
+        if (ahi > p.off_ring || (uint32_t)st.tmem_col + st.n > 512u) return 6;
+        for (int i = 0; i < nw; ++i)
+            if (writes[i].lo < ahi && alo < writes[i].hi && writes[i].ev >= (int)st.wait_ev) return 4;
+        for (int i = 0; i < nr; ++i)
+            if (reads[i].lo < (uint32_t)st.tmem_col + st.n && (uint32_t)st.tmem_col < reads[i].hi && reads[i].ev >= (int)st.wait_ev) return 5;
+        if (st.epi == 1 || st.epi == 2) {
+            const int e = produced++;
+            if (e >= 2 && (int)st.wait_ev < e - 1) return 3;
+            if (st.out_off + (uint32_t)st.n * kTcM * 2u > p.off_ring) return 6;
+            writes[nw++] = {st.out_off, st.out_off + (uint32_t)st.n * kTcM * 2u, e};
+            reads[nr++] = {st.tmem_col, (uint32_t)st.tmem_col + st.n, e};
+        }
+    }
+    if (p.nsteps == 0 || p.st[p.nsteps - 1].epi != 3) return 7;
+    return 0;
+}
 extern "C" size_t pcst_noise_predictor_workspace_bytes(int B, int feature_dim, int nblocks) {
     if (B <= 0 || feature_dim <= 0 || nblocks < 0) return 0;
     return align_up((size_t)B * (nblocks + 1) * feature_dim * sizeof(float), 256);

@@ -109,6 +109,17 @@ def test_denoiser_plan_queries_are_host_only(lib):
     assert lib.pcst_chamfer_shard_payload_floats(120000) == 120000 + 256
 
 
+def test_denoiser_step_table_is_consistent_for_every_supported_size(lib):
+    """The fused denoiser's schedule (MMA steps running one hidden chunk ahead of the epilogues, events alternating between
+    two mbarriers) is derived on the host from the buffers each step touches; the library's self-check replays it for every
+    feature width and block count the kernel accepts -- including hidden layers that split into 1, 2, 3 or 4 chunks and
+    sizes no GPU test runs -- and reports the first violated dependency rule (deadlock, parity ambiguity, RAW, WAR, range)."""
+    for F in range(16, 257, 16):
+        for nb in range(0, 9):
+            assert lib.pcst_noise_predictor_plan_selfcheck(F, 128, nb) == 0, (F, nb)
+    assert lib.pcst_noise_predictor_plan_selfcheck(250, 128, 6) == -1
+
+
 def test_tuning_knobs(lib):
     _lib.set_tuning("nn_min.splits", 3)
     assert _lib.get_tuning("nn_min.splits") == 3

@@ -929,10 +929,12 @@ def test_noise_predictor_fused_kernel_against_reference_golden(api, dev, golden)
     np.testing.assert_allclose(plain, g["out"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("B,N,F,T", [(2, 30000, 256, 128), (3, 1000, 256, 128), (1, 77, 128, 64), (2, 500, 48, 16)])
+@pytest.mark.parametrize("B,N,F,T", [(2, 30000, 256, 128), (3, 1000, 256, 128), (1, 77, 128, 64), (2, 500, 48, 16),
+                                     (1, 300, 144, 32), (2, 200, 208, 64), (1, 130, 16, 8)])
 def test_noise_predictor_fused_kernel_against_linear_stack(api, dev, B, N, F, T):
     """Default configuration (feature_dim 256, time_embed_dim 128) at the coarse-cloud size of the sampling loop, rows that
-    do not fill the last tile, and narrower feature widths: fused kernel vs the module's own nn.Linear formulation in
+    do not fill the last tile, narrower feature widths, and widths whose hidden layer splits into uneven chunks (144: 128 +
+    128 + 32 columns; 208: 128 + 128 + 128 + 32): fused kernel vs the module's own nn.Linear formulation in
     fp32 (which is the reference's, see the golden test), rtol 2e-2 / atol 2e-2."""
     torch.manual_seed(9)
     net = api.dm.NoisePredictor(_noise_cfg(F, T)).to(dev).eval()
